@@ -1,0 +1,125 @@
+/* C-ABI of the B200 batched gripper simulator (libgripper_sim_b200.so).
+ *
+ * The reference has no FFI of its own for this path: RobotEnv (python) talks to dm_control's `Physics`
+ * (python) which wraps libmujoco.  This header is therefore the boundary a maintainer binds INSTEAD of
+ * `dm_control.mujoco.Physics` + the per-environment python loop; each entry point cites the reference
+ * interface it replaces.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *   - one handle per GPU; a handle is not thread-safe; every call runs on the handle's own CUDA stream
+ *     unless a `stream` argument (a cudaStream_t passed as void*) is given (NULL = the handle's stream)
+ *   - functions return 0 on success, non-zero on error; grs_last_error() returns the message
+ *   - *_dev pointers are device pointers, *_host pointers are host pointers (pinned memory is faster)
+ *   - arrays are env-major: actions[N][A], obs[N][C][H][W], goals[N][2]
+ */
+#ifndef B200_GRIPPER_SIM_H
+#define B200_GRIPPER_SIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct grs_sim grs_sim;
+
+/* Environment constructor contract = the fields RobotEnv reads from its config Namespace
+ * (reference config/base_config.py:13-43; defaults in grs_default_config). */
+typedef struct grs_config {
+  int32_t max_steps;        /* base_config.py:36  substeps allowed per phase of an agent step (400) */
+  int32_t time_horizon;     /* base_config.py:43  agent steps per episode (400) */
+  int32_t include_roll;     /* base_config.py:33  action dim 6 (1) or 5 (0) */
+  int32_t full_observation; /* base_config.py:22  RGB-D+pad (5 channels) or RGB+pad (4) */
+  int32_t im_reward;        /* base_config.py:38  add the intrinsic (KL) reward, reward.py:57-77 */
+  int32_t her_buffer;       /* base_config.py:39  add exp(-|dg-ag|), robot_env.py:268-271 */
+  int32_t direction;        /* base_config.py:42  0 -> (1,0), 45 -> (1,1), robot_env.py:30-33 */
+  int32_t width, height;    /* base_config.py:18-19 observation size (64 x 64) */
+  int32_t auto_reset;       /* SB3 VecEnv semantics: reset an environment in the step that ends its episode */
+  float pos_tolerance;      /* base_config.py:32 (0.002) */
+  float grasp_tolerance;    /* base_config.py:31 (0.03) */
+  float max_translation;    /* base_config.py:30 (0.05) */
+  float max_rotation;       /* base_config.py:29 (0.15) */
+} grs_config;
+
+/* per-environment step record written by grs_step (robot_env.py:226-241 `info` + the return tuple) */
+enum {
+  GRS_INFO_REWARD = 0, GRS_INFO_DONE, GRS_INFO_STATUS, GRS_INFO_GRASP, GRS_INFO_PHEROMONE, GRS_INFO_OBJECT_GRASPED,
+  GRS_INFO_GRIPPER_OPEN, GRS_INFO_REACHED_TARGET, GRS_INFO_REACHED_INITIAL, GRS_INFO_FAIL, GRS_INFO_NSUB_A,
+  GRS_INFO_NSUB_B, GRS_INFO_NSUB_C, GRS_INFO_TOTAL_DISTANCE, GRS_INFO_LINE_DISTANCE, GRS_INFO_INIT_OBJ_POS /*3*/,
+  GRS_INFO_FINAL_OBJ_POS = 18 /*3*/, GRS_INFO_GRIPPER_POS = 21 /*3*/, GRS_INFO_ACHIEVED = 24 /*2*/, GRS_INFO_DESIRED = 26 /*2*/,
+  GRS_INFO_SOLVER_ITERS = 28, GRS_INFO_NCON_MAX, GRS_INFO_FLAGS, GRS_INFO_EPISODE_STEP, GRS_INFO_STRIDE = 32
+};
+enum { GRS_STATE_STRIDE = 64 }; /* floats per environment in the packed state record */
+enum { GRS_STATUS_RUNNING = 0, GRS_STATUS_FAIL = 1, GRS_STATUS_TIME_LIMIT = 2 }; /* robot_env.py:19-22 */
+
+const char* grs_last_error(void);
+void grs_default_config(grs_config* cfg);
+
+/* replaces mujoco.Physics.from_xml_path(...) + RobotEnv.__init__ (robot_env.py:24-44) for num_envs instances */
+grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs_config* cfg, int32_t device);
+void grs_destroy(grs_sim* sim);
+
+int32_t grs_num_envs(const grs_sim* sim);
+int32_t grs_action_dim(const grs_sim* sim);               /* actuator.py:236-243 */
+int32_t grs_obs_shape(const grs_sim* sim, int32_t* chw);  /* sensor.py:12-54 */
+void* grs_stream(const grs_sim* sim);                     /* cudaStream_t of the handle */
+
+/* replaces RobotEnv.reset (robot_env.py:56-75) for the environments whose mask byte is non-zero (NULL = all) */
+int32_t grs_reset(grs_sim* sim, const uint8_t* mask_dev, void* stream);
+
+/* replaces RobotEnv.step (robot_env.py:77-241) for all environments: one fused agent step.
+ * Results land in the handle's device buffers (grs_buffer). */
+int32_t grs_step(grs_sim* sim, const float* actions_dev, void* stream);
+
+/* the same through HOST buffers (the call a VecEnv makes): H2D of actions, the step, D2H of results.
+ * Any output pointer may be NULL.  info_host receives N x GRS_INFO_STRIDE floats. */
+int32_t grs_step_host(grs_sim* sim, const float* actions_host, uint8_t* obs_host, float* achieved_host,
+                      float* desired_host, float* reward_host, uint8_t* done_host, float* info_host,
+                      uint8_t* terminal_obs_host);
+int32_t grs_reset_host(grs_sim* sim, uint8_t* obs_host, float* achieved_host, float* desired_host);
+
+/* replaces n x physics.step() with the controls currently in the state (robot_env.py:100) — parity tests */
+int32_t grs_substep(grs_sim* sim, int32_t n, void* stream);
+
+/* named device buffers: "state" f32[N][64], "info" f32[N][32], "obs" u8[N][C][H][W], "terminal_obs" (same),
+ * "reward" f32[N], "done" u8[N], "achieved" f32[N][2], "desired" f32[N][2], "render_state" f32[N][96],
+ * "debug" f32[N][GRS_DEBUG_STRIDE].  Returns 0 and fills ptr/bytes, or non-zero for an unknown name. */
+int32_t grs_buffer(grs_sim* sim, const char* name, void** ptr, uint64_t* bytes);
+
+/* physics.data.qpos/qvel/ctrl/qacc_warmstart + the env flags, as host arrays [N][14],[N][13],[N][7],[N][13],[N][3]
+ * (gripper_open, episode_step, status).  Any pointer may be NULL. */
+int32_t grs_get_state(grs_sim* sim, float* qpos, float* qvel, float* ctrl, float* warmstart, int32_t* flags);
+int32_t grs_set_state(grs_sim* sim, const float* qpos, const float* qvel, const float* ctrl, const float* warmstart, const int32_t* flags);
+
+/* physics.data.ncon / contact[i].geom1/geom2/dist/pos/frame at the current state (actuator.py:157-176).
+ * Host arrays ncon[N], geom[N][K][2], dist[N][K], pos[N][K][3], frame[N][K][9] with K = grs_max_contacts(). */
+int32_t grs_max_contacts(void);
+int32_t grs_get_contacts(grs_sim* sim, int32_t* ncon, int32_t* geom, float* dist, float* pos, float* frame);
+
+/* one physics.step() on every environment with a dump of the intermediate quantities of environment
+ * state (M, qfrc_bias, qfrc_smooth, qacc_smooth, efc rows, qacc, ...) into the "debug" buffer */
+enum { GRS_DEBUG_STRIDE = 2048 };
+int32_t grs_debug_step(grs_sim* sim);
+
+/* compiled-model constants for compiler parity (mjModel fields). Returns the number of doubles written,
+ * or the required count when out == NULL, or -1 for an unknown name.  Names: body_mass, body_ipos, body_iquat,
+ * body_inertia, body_invweight0, dof_invweight0, dof_armature, dof_damping, geom_pos, geom_quat, geom_rbound,
+ * geom_friction, qpos0, meaninertia, extent, hull_verts:<mesh>, body_pos, body_quat, jnt_axis, jnt_range ... */
+int64_t grs_model_get(const grs_sim* sim, const char* name, double* out, int64_t cap);
+int64_t grs_model_get_int(const grs_sim* sim, const char* name, int32_t* out, int64_t cap);
+/* compile only (no GPU needed): returns a model handle usable with grs_model_get*, free with grs_destroy */
+grs_sim* grs_compile_only(const char* xml_path);
+
+/* replaces RobotEnv.render / physics.render(camera_id,w,h[,depth]) (sensor.py:64-73) for every environment:
+ * rgb u8[N][h][w][3] and depth f32[N][h][w] (metres) device buffers; either may be NULL */
+int32_t grs_render(grs_sim* sim, int32_t camera_id, int32_t width, int32_t height, uint8_t* rgb_dev, float* depth_dev, void* stream);
+
+/* number of kernels launched by this handle since creation (bench.py reports it as gpu_launches) */
+uint64_t grs_launch_count(const grs_sim* sim);
+/* average device time (ms) of the fused step kernel over the launches since the last call (CUDA events on the stream) */
+float grs_step_kernel_ms(grs_sim* sim, int32_t reset_counters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
