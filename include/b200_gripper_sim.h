@@ -21,6 +21,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define GRS_API __attribute__((visibility("default")))
+#else
+#define GRS_API
+#endif
+
 typedef struct grs_sim grs_sim;
 
 /* Environment constructor contract = the fields RobotEnv reads from its config Namespace
@@ -47,77 +53,89 @@ enum {
   GRS_INFO_GRIPPER_OPEN, GRS_INFO_REACHED_TARGET, GRS_INFO_REACHED_INITIAL, GRS_INFO_FAIL, GRS_INFO_NSUB_A,
   GRS_INFO_NSUB_B, GRS_INFO_NSUB_C, GRS_INFO_TOTAL_DISTANCE, GRS_INFO_LINE_DISTANCE, GRS_INFO_INIT_OBJ_POS /*3*/,
   GRS_INFO_FINAL_OBJ_POS = 18 /*3*/, GRS_INFO_GRIPPER_POS = 21 /*3*/, GRS_INFO_ACHIEVED = 24 /*2*/, GRS_INFO_DESIRED = 26 /*2*/,
-  GRS_INFO_SOLVER_ITERS = 28, GRS_INFO_NCON_MAX, GRS_INFO_FLAGS, GRS_INFO_EPISODE_STEP, GRS_INFO_STRIDE = 32
+  GRS_INFO_SOLVER_ITERS = 28 /* Newton iterations summed over the substeps */, GRS_INFO_NCON_MAX,
+  GRS_INFO_FLAGS /* bit 0: contact buffer overflowed, bit 1: non-finite state was reset */, GRS_INFO_EPISODE_STEP,
+  GRS_INFO_EPISODE_RETURN = 32 /* Monitor `r` */, GRS_INFO_EPISODE_SUBSTEPS, GRS_INFO_TARGET_QPOS = 34 /*5*/, GRS_INFO_STRIDE = 40
 };
-enum { GRS_STATE_STRIDE = 64 }; /* floats per environment in the packed state record */
+/* packed per-environment state record ("state" buffer), floats */
+enum {
+  GRS_ST_QPOS = 0 /*14*/, GRS_ST_QVEL = 14 /*13*/, GRS_ST_CTRL = 27 /*7*/, GRS_ST_WARMSTART = 34 /*13*/, GRS_ST_GRIPPER_OPEN = 47,
+  GRS_ST_EPISODE_STEP = 48, GRS_ST_STATUS = 49, GRS_ST_XFRC_Z = 50 /* xfrc_applied["ee",2], robot_env.py:65 */,
+  GRS_ST_EPISODE_RETURN = 51, GRS_ST_EPISODE_SUBSTEPS = 52, GRS_STATE_STRIDE = 64
+};
+enum { GRS_RENDER_STATE_STRIDE = 96 }; /* 7 geoms x (pos 3 + mat 9) then the gripper camera (pos 3 + mat 9) */
 enum { GRS_STATUS_RUNNING = 0, GRS_STATUS_FAIL = 1, GRS_STATUS_TIME_LIMIT = 2 }; /* robot_env.py:19-22 */
 
-const char* grs_last_error(void);
-void grs_default_config(grs_config* cfg);
+GRS_API const char* grs_last_error(void);
+GRS_API void grs_default_config(grs_config* cfg);
 
 /* replaces mujoco.Physics.from_xml_path(...) + RobotEnv.__init__ (robot_env.py:24-44) for num_envs instances */
-grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs_config* cfg, int32_t device);
-void grs_destroy(grs_sim* sim);
+GRS_API grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs_config* cfg, int32_t device);
+GRS_API void grs_destroy(grs_sim* sim);
 
-int32_t grs_num_envs(const grs_sim* sim);
-int32_t grs_action_dim(const grs_sim* sim);               /* actuator.py:236-243 */
-int32_t grs_obs_shape(const grs_sim* sim, int32_t* chw);  /* sensor.py:12-54 */
-void* grs_stream(const grs_sim* sim);                     /* cudaStream_t of the handle */
+GRS_API int32_t grs_num_envs(const grs_sim* sim);
+GRS_API int32_t grs_action_dim(const grs_sim* sim);               /* actuator.py:236-243 */
+GRS_API int32_t grs_obs_shape(const grs_sim* sim, int32_t* chw);  /* sensor.py:12-54 */
+GRS_API void* grs_stream(const grs_sim* sim);                     /* cudaStream_t of the handle */
 
 /* replaces RobotEnv.reset (robot_env.py:56-75) for the environments whose mask byte is non-zero (NULL = all) */
-int32_t grs_reset(grs_sim* sim, const uint8_t* mask_dev, void* stream);
+GRS_API int32_t grs_reset(grs_sim* sim, const uint8_t* mask_dev, void* stream);
 
 /* replaces RobotEnv.step (robot_env.py:77-241) for all environments: one fused agent step.
  * Results land in the handle's device buffers (grs_buffer). */
-int32_t grs_step(grs_sim* sim, const float* actions_dev, void* stream);
+GRS_API int32_t grs_step(grs_sim* sim, const float* actions_dev, void* stream);
 
 /* the same through HOST buffers (the call a VecEnv makes): H2D of actions, the step, D2H of results.
  * Any output pointer may be NULL.  info_host receives N x GRS_INFO_STRIDE floats. */
-int32_t grs_step_host(grs_sim* sim, const float* actions_host, uint8_t* obs_host, float* achieved_host,
+GRS_API int32_t grs_step_host(grs_sim* sim, const float* actions_host, uint8_t* obs_host, float* achieved_host,
                       float* desired_host, float* reward_host, uint8_t* done_host, float* info_host,
                       uint8_t* terminal_obs_host);
-int32_t grs_reset_host(grs_sim* sim, uint8_t* obs_host, float* achieved_host, float* desired_host);
+GRS_API int32_t grs_reset_host(grs_sim* sim, uint8_t* obs_host, float* achieved_host, float* desired_host);
 
 /* replaces n x physics.step() with the controls currently in the state (robot_env.py:100) — parity tests */
-int32_t grs_substep(grs_sim* sim, int32_t n, void* stream);
+GRS_API int32_t grs_substep(grs_sim* sim, int32_t n, void* stream);
 
-/* named device buffers: "state" f32[N][64], "info" f32[N][32], "obs" u8[N][C][H][W], "terminal_obs" (same),
+/* named device buffers: "state" f32[N][64], "info" f32[N][40], "obs" u8[N][C][H][W], "terminal_obs" (same),
  * "reward" f32[N], "done" u8[N], "achieved" f32[N][2], "desired" f32[N][2], "render_state" f32[N][96],
  * "debug" f32[N][GRS_DEBUG_STRIDE].  Returns 0 and fills ptr/bytes, or non-zero for an unknown name. */
-int32_t grs_buffer(grs_sim* sim, const char* name, void** ptr, uint64_t* bytes);
+GRS_API int32_t grs_buffer(grs_sim* sim, const char* name, void** ptr, uint64_t* bytes);
 
 /* physics.data.qpos/qvel/ctrl/qacc_warmstart + the env flags, as host arrays [N][14],[N][13],[N][7],[N][13],[N][3]
- * (gripper_open, episode_step, status).  Any pointer may be NULL. */
-int32_t grs_get_state(grs_sim* sim, float* qpos, float* qvel, float* ctrl, float* warmstart, int32_t* flags);
-int32_t grs_set_state(grs_sim* sim, const float* qpos, const float* qvel, const float* ctrl, const float* warmstart, const int32_t* flags);
+ * (gripper_open, episode_step, status), xfrc_z[N].  Any pointer may be NULL. */
+GRS_API int32_t grs_get_state(grs_sim* sim, float* qpos, float* qvel, float* ctrl, float* warmstart, int32_t* flags, float* xfrc_z);
+GRS_API int32_t grs_set_state(grs_sim* sim, const float* qpos, const float* qvel, const float* ctrl, const float* warmstart, const int32_t* flags,
+                      const float* xfrc_z);
 
 /* physics.data.ncon / contact[i].geom1/geom2/dist/pos/frame at the current state (actuator.py:157-176).
  * Host arrays ncon[N], geom[N][K][2], dist[N][K], pos[N][K][3], frame[N][K][9] with K = grs_max_contacts(). */
-int32_t grs_max_contacts(void);
-int32_t grs_get_contacts(grs_sim* sim, int32_t* ncon, int32_t* geom, float* dist, float* pos, float* frame);
+GRS_API int32_t grs_max_contacts(void);
+GRS_API int32_t grs_get_contacts(grs_sim* sim, int32_t* ncon, int32_t* geom, float* dist, float* pos, float* frame);
 
 /* one physics.step() on every environment with a dump of the intermediate quantities of environment
  * state (M, qfrc_bias, qfrc_smooth, qacc_smooth, efc rows, qacc, ...) into the "debug" buffer */
 enum { GRS_DEBUG_STRIDE = 2048 };
-int32_t grs_debug_step(grs_sim* sim);
+GRS_API int32_t grs_debug_step(grs_sim* sim);
 
 /* compiled-model constants for compiler parity (mjModel fields). Returns the number of doubles written,
  * or the required count when out == NULL, or -1 for an unknown name.  Names: body_mass, body_ipos, body_iquat,
  * body_inertia, body_invweight0, dof_invweight0, dof_armature, dof_damping, geom_pos, geom_quat, geom_rbound,
  * geom_friction, qpos0, meaninertia, extent, hull_verts:<mesh>, body_pos, body_quat, jnt_axis, jnt_range ... */
-int64_t grs_model_get(const grs_sim* sim, const char* name, double* out, int64_t cap);
-int64_t grs_model_get_int(const grs_sim* sim, const char* name, int32_t* out, int64_t cap);
+GRS_API int64_t grs_model_get(const grs_sim* sim, const char* name, double* out, int64_t cap);
+GRS_API int64_t grs_model_get_int(const grs_sim* sim, const char* name, int32_t* out, int64_t cap);
+/* names of the model's bodies / geoms / joints / cameras / meshes (kind = "body" ...), '\n'-separated, NUL-terminated;
+ * returns the buffer size needed */
+GRS_API int64_t grs_model_names(const grs_sim* sim, const char* kind, char* out, int64_t cap);
 /* compile only (no GPU needed): returns a model handle usable with grs_model_get*, free with grs_destroy */
-grs_sim* grs_compile_only(const char* xml_path);
+GRS_API grs_sim* grs_compile_only(const char* xml_path);
 
 /* replaces RobotEnv.render / physics.render(camera_id,w,h[,depth]) (sensor.py:64-73) for every environment:
  * rgb u8[N][h][w][3] and depth f32[N][h][w] (metres) device buffers; either may be NULL */
-int32_t grs_render(grs_sim* sim, int32_t camera_id, int32_t width, int32_t height, uint8_t* rgb_dev, float* depth_dev, void* stream);
+GRS_API int32_t grs_render(grs_sim* sim, int32_t camera_id, int32_t width, int32_t height, uint8_t* rgb_dev, float* depth_dev, void* stream);
 
 /* number of kernels launched by this handle since creation (bench.py reports it as gpu_launches) */
-uint64_t grs_launch_count(const grs_sim* sim);
+GRS_API uint64_t grs_launch_count(const grs_sim* sim);
 /* average device time (ms) of the fused step kernel over the launches since the last call (CUDA events on the stream) */
-float grs_step_kernel_ms(grs_sim* sim, int32_t reset_counters);
+GRS_API float grs_step_kernel_ms(grs_sim* sim, int32_t reset_counters);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,50 @@
+"""Build the native library (nvcc, sm_100a) in-tree: mujoco_rl_manipulate_unknown_objects_b200/libgripper_sim_b200.so.
+
+The build container has no GPU; nvcc cross-compiles.  The .so is git-ignored but travels to the GPU box with the
+repository snapshot.  `python -m mujoco_rl_manipulate_unknown_objects_b200.build` rebuilds when a source is newer.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libgripper_sim_b200.so")
+SOURCES = ["gripper_sim.cu", "policy_kernels.cu", "mjcf_compiler.cpp", "dev_model.cpp"]
+HEADERS = ["model.h", "sim_kernels.cuh", "env_kernels.cuh", "render_kernels.cuh", "policy_kernels.cuh",
+           os.path.join("..", "..", "include", "b200_gripper_sim.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+              "-Xcompiler", "-fvisibility=hidden", "-shared", "-diag-suppress", "550"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    files = [os.path.join(CSRC, f) for f in SOURCES + HEADERS if os.path.exists(os.path.join(CSRC, f))]
+    return any(os.path.getmtime(f) > t for f in files)
+
+
+def build_native(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + srcs
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout)
+    if verbose:
+        print(r.stdout)
+    os.replace(LIB + ".tmp", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

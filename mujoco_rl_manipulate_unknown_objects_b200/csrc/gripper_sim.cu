@@ -1,0 +1,529 @@
+// libgripper_sim_b200.so — the C-ABI of include/b200_gripper_sim.h on top of the sm_100a kernels.
+//
+// Host side only owns buffers, the CUDA stream and launch bookkeeping; every per-environment computation is in
+// env_kernels.cuh / sim_kernels.cuh / render_kernels.cuh.  There is no CPU fallback: without a CUDA device
+// grs_create fails (grs_compile_only, the model compiler, is the one entry point that works without a GPU).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_gripper_sim.h"
+#include "env_kernels.cuh"
+#include "render_kernels.cuh"
+
+using namespace grs;
+
+static_assert(GRS_INFO_STRIDE == IN_STRIDE && GRS_STATE_STRIDE == ST_STRIDE && GRS_DEBUG_STRIDE == DEBUG_STRIDE && GRS_RENDER_STATE_STRIDE == RS_STRIDE,
+              "header / kernel record layouts diverged");
+static_assert(GRS_ST_XFRC_Z == ST_XFRC_Z && GRS_INFO_TARGET_QPOS == IN_TARGET_QPOS && GRS_INFO_EPISODE_RETURN == IN_EPISODE_RETURN, "record layouts diverged");
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) { g_err = msg; return 1; }
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct grs_sim {
+  HostModel hm;
+  bool compile_only = false;
+  int n = 0, device = 0, C = 5, H = 64, W = 64, adim = 6;
+  grs_config cfg{};
+  EnvCfg ecfg{};
+  cudaStream_t stream = nullptr;
+  SimBuffers b{};
+  RenderScene scene{};
+  DevModel* d_model = nullptr;
+  float4* d_hull = nullptr;
+  int* d_adj = nullptr;
+  unsigned char *d_obs = nullptr, *d_terminal_obs = nullptr, *d_reset_obs = nullptr;
+  float* d_actions = nullptr;
+  float* d_hist = nullptr;  // [N][2][256] histograms of the previous observation (intrinsic reward)
+  std::vector<void*> owned;
+  uint64_t launches = 0;
+  // timing of the fused step kernel
+  static constexpr int NEV = 64;
+  cudaEvent_t ev0[NEV]{}, ev1[NEV]{};
+  int ev_n = 0;
+  double ms_sum = 0;
+  long ms_cnt = 0;
+  int grid = 0;
+  size_t smem = 0;
+};
+
+template <class T>
+static T* dalloc(grs_sim* s, size_t count) {
+  void* p = nullptr;
+  CU(cudaMalloc(&p, count * sizeof(T)));
+  CU(cudaMemset(p, 0, count * sizeof(T)));
+  s->owned.push_back(p);
+  return (T*)p;
+}
+
+extern "C" const char* grs_last_error(void) { return g_err.c_str(); }
+
+extern "C" void grs_default_config(grs_config* c) {
+  if (!c) return;
+  c->max_steps = 400; c->time_horizon = 400; c->include_roll = 1; c->full_observation = 1; c->im_reward = 0; c->her_buffer = 0;
+  c->direction = 0; c->width = 64; c->height = 64; c->auto_reset = 1;
+  c->pos_tolerance = 0.002f; c->grasp_tolerance = 0.03f; c->max_translation = 0.05f; c->max_rotation = 0.15f;
+}
+
+extern "C" grs_sim* grs_compile_only(const char* xml_path) {
+  try {
+    auto s = std::make_unique<grs_sim>();
+    s->hm = compile_mjcf(xml_path ? xml_path : "");
+    s->compile_only = true;
+    return s.release();
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
+static void harvest_events(grs_sim* s) {
+  for (int i = 0; i < s->ev_n; i++) {
+    float ms = 0;
+    if (cudaEventSynchronize(s->ev1[i]) == cudaSuccess && cudaEventElapsedTime(&ms, s->ev0[i], s->ev1[i]) == cudaSuccess) { s->ms_sum += ms; s->ms_cnt++; }
+  }
+  s->ev_n = 0;
+}
+
+static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, sizeof(int), st)); }
+
+extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs_config* cfg_in, int32_t device) {
+  grs_sim* raw = nullptr;
+  try {
+    if (num_envs <= 0) throw std::runtime_error("num_envs must be positive");
+    grs_config cfg;
+    if (cfg_in) cfg = *cfg_in; else grs_default_config(&cfg);
+    if (cfg.direction != 0 && cfg.direction != 45) throw std::runtime_error("direction must be 0 or 45 (robot_env.py:30-33)");
+    if (cfg.width <= 0 || cfg.height <= 0 || cfg.width > 256 || cfg.height > 256) throw std::runtime_error("observation size must be within 1..256");
+    if (cfg.max_steps <= 0 || cfg.time_horizon <= 0) throw std::runtime_error("max_steps and time_horizon must be positive");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device available: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) throw std::runtime_error("invalid CUDA device index");
+    auto s = std::make_unique<grs_sim>();
+    raw = s.get();
+    s->hm = compile_mjcf(xml_path ? xml_path : "");
+    s->n = num_envs; s->device = device; s->cfg = cfg;
+    s->C = cfg.full_observation ? 5 : 4; s->H = cfg.height; s->W = cfg.width; s->adim = cfg.include_roll ? 6 : 5;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    DevModel dm;
+    std::vector<float> hv;
+    std::vector<int> adj;
+    build_dev_model(s->hm, dm, hv, adj);
+    s->d_model = dalloc<DevModel>(s.get(), 1);
+    CU(cudaMemcpy(s->d_model, &dm, sizeof dm, cudaMemcpyHostToDevice));
+    s->d_hull = dalloc<float4>(s.get(), hv.size() / 4 + 1);
+    CU(cudaMemcpy(s->d_hull, hv.data(), hv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    s->d_adj = dalloc<int>(s.get(), adj.size() + 1);
+    CU(cudaMemcpy(s->d_adj, adj.data(), adj.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const size_t N = num_envs;
+    SimBuffers& b = s->b;
+    b.n = num_envs; b.model = s->d_model; b.hull = s->d_hull; b.adj = s->d_adj;
+    b.state = dalloc<float>(s.get(), N * ST_STRIDE);
+    b.info = dalloc<float>(s.get(), N * IN_STRIDE);
+    b.reward = dalloc<float>(s.get(), N);
+    b.done = dalloc<unsigned char>(s.get(), N);
+    b.achieved = dalloc<float>(s.get(), N * 2);
+    b.desired = dalloc<float>(s.get(), N * 2);
+    b.render_state = dalloc<float>(s.get(), N * RS_STRIDE);
+    b.reset_record = dalloc<float>(s.get(), ST_STRIDE + IN_STRIDE + RS_STRIDE);
+    b.debug = dalloc<float>(s.get(), N * DEBUG_STRIDE);
+    b.queue = dalloc<int>(s.get(), 4);
+    const size_t obs_bytes = (size_t)s->C * s->H * s->W;
+    s->d_obs = dalloc<unsigned char>(s.get(), N * obs_bytes);
+    s->d_terminal_obs = dalloc<unsigned char>(s.get(), N * obs_bytes);
+    s->d_reset_obs = dalloc<unsigned char>(s.get(), obs_bytes);
+    s->d_actions = dalloc<float>(s.get(), N * 6);
+    s->d_hist = dalloc<float>(s.get(), N * 512 + 512);
+    EnvCfg& e = s->ecfg;
+    e.max_steps = cfg.max_steps; e.time_horizon = cfg.time_horizon; e.include_roll = cfg.include_roll; e.her_buffer = cfg.her_buffer;
+    e.im_reward = cfg.im_reward; e.auto_reset = cfg.auto_reset; e.full_observation = cfg.full_observation;
+    e.obs_cam = 0;
+    for (int c = 0; c < s->hm.ncam; c++) if (s->hm.cam_names[c] == "gripper_camera") e.obs_cam = c;  // robot_env.py:281
+    e.dir[0] = 1.0f; e.dir[1] = cfg.direction == 45 ? 1.0f : 0.0f;
+    e.pos_tol = cfg.pos_tolerance; e.grasp_tol = cfg.grasp_tolerance; e.max_trans = cfg.max_translation; e.max_rot = cfg.max_rotation;
+    // launch geometry: persistent blocks, as many as fit (one WS per warp in shared memory)
+    s->smem = smem_bytes();
+    CU(cudaFuncSetAttribute(k_env_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    CU(cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    CU(cudaFuncSetAttribute(k_contacts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    CU(cudaFuncSetAttribute(k_debug_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    CU(cudaFuncSetAttribute(k_make_reset_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    int per_sm = 0, nsm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step, WARPS_PER_BLOCK * 32, s->smem));
+    CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    if (per_sm < 1) throw std::runtime_error("step kernel does not fit on this device");
+    int want = (num_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    s->grid = std::min(want, per_sm * nsm);
+    for (int i = 0; i < grs_sim::NEV; i++) { CU(cudaEventCreate(&s->ev0[i])); CU(cudaEventCreate(&s->ev1[i])); }
+    render_scene_upload(s->hm, s->scene, s->owned);
+    // the reset record and the observation of a freshly reset environment (identical for every env and every episode)
+    k_make_reset_record<<<1, 32, s->smem, s->stream>>>(s->b, s->ecfg);
+    CU(cudaGetLastError());
+    s->launches++;
+    launch_render_obs(s->scene, s->b.reset_record + ST_STRIDE + IN_STRIDE, s->b.reset_record + ST_STRIDE, nullptr, nullptr, s->d_reset_obs, nullptr, nullptr,
+                      s->d_hist + N * 512, nullptr, 1, s->C, s->H, s->W, s->hm.cam_fovy[e.obs_cam], 0, 0, s->stream);
+    s->launches++;
+    CU(cudaStreamSynchronize(s->stream));
+    if (grs_reset(s.get(), nullptr, nullptr) != 0) throw std::runtime_error(g_err);
+    CU(cudaStreamSynchronize(s->stream));
+    return s.release();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    (void)raw;
+    return nullptr;
+  }
+}
+
+extern "C" void grs_destroy(grs_sim* s) {
+  if (!s) return;
+  if (!s->compile_only) {
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void* p : s->owned) cudaFree(p);
+    for (int i = 0; i < grs_sim::NEV; i++) { if (s->ev0[i]) cudaEventDestroy(s->ev0[i]); if (s->ev1[i]) cudaEventDestroy(s->ev1[i]); }
+    if (s->stream) cudaStreamDestroy(s->stream);
+  }
+  delete s;
+}
+
+extern "C" int32_t grs_num_envs(const grs_sim* s) { return s ? s->n : 0; }
+extern "C" int32_t grs_action_dim(const grs_sim* s) { return s ? s->adim : 0; }
+extern "C" int32_t grs_obs_shape(const grs_sim* s, int32_t* chw) {
+  if (!s || !chw) return fail("null argument");
+  chw[0] = s->C; chw[1] = s->H; chw[2] = s->W;
+  return 0;
+}
+extern "C" void* grs_stream(const grs_sim* s) { return s ? (void*)s->stream : nullptr; }
+
+#define GUARD(s)                                                          \
+  if (!(s)) return fail("null simulator handle");                         \
+  if ((s)->compile_only) return fail("handle was created by grs_compile_only: no device state");
+
+extern "C" int32_t grs_reset(grs_sim* s, const uint8_t* mask_dev, void* stream) {
+  GUARD(s);
+  try {
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const int wpb = 8;
+    k_reset<<<(s->n + wpb - 1) / wpb, wpb * 32, 0, st>>>(s->b, mask_dev);
+    CU(cudaGetLastError());
+    launch_copy_reset_obs(s->d_obs, s->d_reset_obs, s->d_hist, s->d_hist + (size_t)s->n * 512, mask_dev, s->n, s->C * s->H * s->W, st);
+    s->launches += 2;
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" int32_t grs_step(grs_sim* s, const float* actions_dev, void* stream) {
+  GUARD(s);
+  if (!actions_dev) return fail("actions pointer is null");
+  try {
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    launch_queue_kernel_prep(s, st);
+    if (s->ev_n == grs_sim::NEV) harvest_events(s);
+    CU(cudaEventRecord(s->ev0[s->ev_n], st));
+    k_env_step<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s->ev1[s->ev_n], st));
+    s->ev_n++;
+    launch_render_obs(s->scene, s->b.render_state, s->b.info, s->b.done, s->b.reward, s->d_obs, s->d_terminal_obs, s->d_reset_obs, s->d_hist,
+                      s->d_hist + (size_t)s->n * 512, s->n, s->C, s->H, s->W, s->hm.cam_fovy[s->ecfg.obs_cam], s->ecfg.auto_reset, s->ecfg.im_reward, st);
+    s->launches += 2;
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" int32_t grs_step_host(grs_sim* s, const float* actions_host, uint8_t* obs_host, float* achieved_host, float* desired_host,
+                                 float* reward_host, uint8_t* done_host, float* info_host, uint8_t* terminal_obs_host) {
+  GUARD(s);
+  if (!actions_host) return fail("actions pointer is null");
+  try {
+    CU(cudaSetDevice(s->device));
+    const size_t N = s->n, ob = (size_t)s->C * s->H * s->W;
+    CU(cudaMemcpyAsync(s->d_actions, actions_host, N * s->adim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (grs_step(s, s->d_actions, nullptr) != 0) return 1;
+    if (obs_host) CU(cudaMemcpyAsync(obs_host, s->d_obs, N * ob, cudaMemcpyDeviceToHost, s->stream));
+    if (achieved_host) CU(cudaMemcpyAsync(achieved_host, s->b.achieved, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (desired_host) CU(cudaMemcpyAsync(desired_host, s->b.desired, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (reward_host) CU(cudaMemcpyAsync(reward_host, s->b.reward, N * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (done_host) CU(cudaMemcpyAsync(done_host, s->b.done, N, cudaMemcpyDeviceToHost, s->stream));
+    if (info_host) CU(cudaMemcpyAsync(info_host, s->b.info, N * IN_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (terminal_obs_host) CU(cudaMemcpyAsync(terminal_obs_host, s->d_terminal_obs, N * ob, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" int32_t grs_reset_host(grs_sim* s, uint8_t* obs_host, float* achieved_host, float* desired_host) {
+  GUARD(s);
+  try {
+    if (grs_reset(s, nullptr, nullptr) != 0) return 1;
+    const size_t N = s->n, ob = (size_t)s->C * s->H * s->W;
+    if (obs_host) CU(cudaMemcpyAsync(obs_host, s->d_obs, N * ob, cudaMemcpyDeviceToHost, s->stream));
+    if (achieved_host) CU(cudaMemcpyAsync(achieved_host, s->b.achieved, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (desired_host) CU(cudaMemcpyAsync(desired_host, s->b.desired, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" int32_t grs_substep(grs_sim* s, int32_t n, void* stream) {
+  GUARD(s);
+  if (n < 0) return fail("negative substep count");
+  try {
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    launch_queue_kernel_prep(s, st);
+    k_substep<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, n);
+    CU(cudaGetLastError());
+    s->launches++;
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" int32_t grs_buffer(grs_sim* s, const char* name, void** ptr, uint64_t* bytes) {
+  GUARD(s);
+  if (!name || !ptr) return fail("null argument");
+  const size_t N = s->n, ob = (size_t)s->C * s->H * s->W;
+  std::string k = name;
+  void* p = nullptr;
+  uint64_t sz = 0;
+  if (k == "state") { p = s->b.state; sz = N * ST_STRIDE * 4; }
+  else if (k == "info") { p = s->b.info; sz = N * IN_STRIDE * 4; }
+  else if (k == "obs") { p = s->d_obs; sz = N * ob; }
+  else if (k == "terminal_obs") { p = s->d_terminal_obs; sz = N * ob; }
+  else if (k == "reset_obs") { p = s->d_reset_obs; sz = ob; }
+  else if (k == "reward") { p = s->b.reward; sz = N * 4; }
+  else if (k == "done") { p = s->b.done; sz = N; }
+  else if (k == "achieved") { p = s->b.achieved; sz = N * 8; }
+  else if (k == "desired") { p = s->b.desired; sz = N * 8; }
+  else if (k == "render_state") { p = s->b.render_state; sz = N * RS_STRIDE * 4; }
+  else if (k == "debug") { p = s->b.debug; sz = N * DEBUG_STRIDE * 4; }
+  else if (k == "actions") { p = s->d_actions; sz = N * 6 * 4; }
+  else return fail("unknown buffer name '" + k + "'");
+  *ptr = p;
+  if (bytes) *bytes = sz;
+  return 0;
+}
+
+extern "C" int32_t grs_get_state(grs_sim* s, float* qpos, float* qvel, float* ctrl, float* warm, int32_t* flags, float* xfrc_z) {
+  GUARD(s);
+  try {
+    CU(cudaSetDevice(s->device));
+    std::vector<float> h((size_t)s->n * ST_STRIDE);
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpy(h.data(), s->b.state, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int e = 0; e < s->n; e++) {
+      const float* r = &h[(size_t)e * ST_STRIDE];
+      if (qpos) std::memcpy(qpos + (size_t)e * NQ, r + ST_QPOS, NQ * 4);
+      if (qvel) std::memcpy(qvel + (size_t)e * NV, r + ST_QVEL, NV * 4);
+      if (ctrl) std::memcpy(ctrl + (size_t)e * NU, r + ST_CTRL, NU * 4);
+      if (warm) std::memcpy(warm + (size_t)e * NV, r + ST_WARM, NV * 4);
+      if (flags) { flags[3 * e] = (int)r[ST_GRIPPER_OPEN]; flags[3 * e + 1] = (int)r[ST_EPISODE_STEP]; flags[3 * e + 2] = (int)r[ST_STATUS]; }
+      if (xfrc_z) xfrc_z[e] = r[ST_XFRC_Z];
+    }
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" int32_t grs_set_state(grs_sim* s, const float* qpos, const float* qvel, const float* ctrl, const float* warm, const int32_t* flags,
+                                 const float* xfrc_z) {
+  GUARD(s);
+  try {
+    CU(cudaSetDevice(s->device));
+    std::vector<float> h((size_t)s->n * ST_STRIDE);
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpy(h.data(), s->b.state, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int e = 0; e < s->n; e++) {
+      float* r = &h[(size_t)e * ST_STRIDE];
+      if (qpos) std::memcpy(r + ST_QPOS, qpos + (size_t)e * NQ, NQ * 4);
+      if (qvel) std::memcpy(r + ST_QVEL, qvel + (size_t)e * NV, NV * 4);
+      if (ctrl) std::memcpy(r + ST_CTRL, ctrl + (size_t)e * NU, NU * 4);
+      if (warm) std::memcpy(r + ST_WARM, warm + (size_t)e * NV, NV * 4);
+      if (flags) { r[ST_GRIPPER_OPEN] = (float)flags[3 * e]; r[ST_EPISODE_STEP] = (float)flags[3 * e + 1]; r[ST_STATUS] = (float)flags[3 * e + 2]; }
+      if (xfrc_z) r[ST_XFRC_Z] = xfrc_z[e];
+    }
+    CU(cudaMemcpy(s->b.state, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" int32_t grs_max_contacts(void) { return MAXCON; }
+
+extern "C" int32_t grs_get_contacts(grs_sim* s, int32_t* ncon, int32_t* geom, float* dist, float* pos, float* frame) {
+  GUARD(s);
+  try {
+    CU(cudaSetDevice(s->device));
+    launch_queue_kernel_prep(s, s->stream);
+    k_contacts<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, s->stream>>>(s->b);
+    CU(cudaGetLastError());
+    s->launches++;
+    CU(cudaStreamSynchronize(s->stream));
+    std::vector<float> h((size_t)s->n * DEBUG_STRIDE);
+    CU(cudaMemcpy(h.data(), s->b.debug, h.size() * 4, cudaMemcpyDeviceToHost));
+    const int K = MAXCON;
+    for (int e = 0; e < s->n; e++) {
+      const float* d = &h[(size_t)e * DEBUG_STRIDE];
+      int nc = (int)d[0];
+      if (ncon) ncon[e] = nc;
+      for (int c = 0; c < K; c++) {
+        const float* o = d + 2 + c * 15;
+        bool live = c < nc;
+        if (geom) { geom[((size_t)e * K + c) * 2] = live ? (int)o[0] : -1; geom[((size_t)e * K + c) * 2 + 1] = live ? (int)o[1] : -1; }
+        if (dist) dist[(size_t)e * K + c] = live ? o[2] : 0;
+        if (pos) for (int k = 0; k < 3; k++) pos[((size_t)e * K + c) * 3 + k] = live ? o[3 + k] : 0;
+        if (frame) for (int k = 0; k < 9; k++) frame[((size_t)e * K + c) * 9 + k] = live ? o[6 + k] : 0;
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" int32_t grs_debug_step(grs_sim* s) {
+  GUARD(s);
+  try {
+    CU(cudaSetDevice(s->device));
+    launch_queue_kernel_prep(s, s->stream);
+    k_debug_step<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, s->stream>>>(s->b);
+    CU(cudaGetLastError());
+    s->launches++;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+// ------------------------------------------------------------------------------------------ model constants
+static const std::vector<double>* model_field(const HostModel& m, const std::string& k) {
+#define F(nm) if (k == #nm) return &m.nm;
+  F(body_mass) F(body_pos) F(body_quat) F(body_ipos) F(body_iquat) F(body_inertia) F(body_invweight0) F(dof_invweight0) F(dof_armature)
+  F(dof_damping) F(geom_pos) F(geom_quat) F(geom_rbound) F(geom_friction) F(geom_margin) F(geom_gap) F(geom_solref) F(geom_solimp) F(geom_rgba) F(geom_size)
+  F(geom_mass) F(qpos0) F(jnt_pos) F(jnt_axis) F(jnt_range) F(act_gear) F(act_ctrlrange) F(cam_pos) F(cam_quat) F(cam_fovy) F(light_pos) F(light_dir)
+#undef F
+  return nullptr;
+}
+static const std::vector<int>* model_field_int(const HostModel& m, const std::string& k) {
+#define F(nm) if (k == #nm) return &m.nm;
+  F(body_parentid) F(body_weldid) F(body_jntadr) F(body_jntnum) F(body_dofadr) F(body_dofnum) F(body_rootid) F(jnt_type) F(jnt_bodyid) F(jnt_qposadr)
+  F(jnt_dofadr) F(jnt_limited) F(dof_bodyid) F(dof_jntid) F(dof_parentid) F(geom_type) F(geom_bodyid) F(geom_meshid) F(geom_condim) F(act_dofid)
+  F(pair_geom1) F(pair_geom2) F(cam_bodyid) F(cam_mode) F(cam_target)
+#undef F
+  return nullptr;
+}
+
+extern "C" int64_t grs_model_get(const grs_sim* s, const char* name, double* out, int64_t cap) {
+  if (!s || !name) return -1;
+  const HostModel& m = s->hm;
+  std::string k = name;
+  std::vector<double> tmp;
+  const std::vector<double>* v = model_field(m, k);
+  if (!v) {
+    if (k == "meaninertia") tmp = {m.meaninertia};
+    else if (k == "extent") tmp = {m.extent};
+    else if (k == "center") tmp = {m.center[0], m.center[1], m.center[2]};
+    else if (k == "timestep") tmp = {m.timestep};
+    else if (k == "impratio") tmp = {m.impratio};
+    else if (k == "tolerance") tmp = {m.tolerance};
+    else if (k == "gravity") tmp = {m.gravity[0], m.gravity[1], m.gravity[2]};
+    else if (k == "znear") tmp = {m.znear};
+    else if (k == "zfar") tmp = {m.zfar};
+    else if (k == "jnt_solref") tmp = {m.jnt_solref[0], m.jnt_solref[1]};
+    else if (k == "jnt_solimp") tmp = {m.jnt_solimp[0], m.jnt_solimp[1], m.jnt_solimp[2], m.jnt_solimp[3], m.jnt_solimp[4]};
+    else if (k.rfind("hull_verts:", 0) == 0 || k.rfind("mesh_pos:", 0) == 0 || k.rfind("mesh_quat:", 0) == 0 || k.rfind("mesh_volume:", 0) == 0 ||
+             k.rfind("mesh_inertia:", 0) == 0) {
+      std::string mn = k.substr(k.find(':') + 1);
+      const HostMesh* hm = nullptr;
+      for (auto& x : m.meshes) if (x.name == mn) hm = &x;
+      if (!hm) return -1;
+      if (k[0] == 'h') tmp = hm->hull_verts;
+      else if (k.rfind("mesh_pos:", 0) == 0) tmp = {hm->pos[0], hm->pos[1], hm->pos[2]};
+      else if (k.rfind("mesh_quat:", 0) == 0) tmp = {hm->quat[0], hm->quat[1], hm->quat[2], hm->quat[3]};
+      else if (k.rfind("mesh_volume:", 0) == 0) tmp = {hm->volume};
+      else tmp = {hm->inertia_unit[0], hm->inertia_unit[1], hm->inertia_unit[2]};
+    } else return -1;
+    v = &tmp;
+  }
+  if (!out) return (int64_t)v->size();
+  int64_t nw = std::min<int64_t>(cap, (int64_t)v->size());
+  for (int64_t i = 0; i < nw; i++) out[i] = (*v)[i];
+  return nw;
+}
+
+extern "C" int64_t grs_model_get_int(const grs_sim* s, const char* name, int32_t* out, int64_t cap) {
+  if (!s || !name) return -1;
+  const HostModel& m = s->hm;
+  std::string k = name;
+  std::vector<int> tmp;
+  const std::vector<int>* v = model_field_int(m, k);
+  if (!v) {
+    if (k == "sizes") tmp = {m.nbody, m.njnt, m.nq, m.nv, m.nu, m.ngeom, m.nmesh, m.npair, m.ncam, m.nlight};
+    else if (k == "iterations") tmp = {m.iterations};
+    else if (k == "cone_elliptic") tmp = {m.cone_elliptic};
+    else if (k == "named_bodies") tmp = {m.body_ee, m.body_object, m.finger1[0], m.finger1[1], m.finger2[0], m.finger2[1]};
+    else if (k.rfind("hull_adjadr:", 0) == 0 || k.rfind("hull_adj:", 0) == 0 || k.rfind("hull_faces:", 0) == 0) {
+      std::string mn = k.substr(k.find(':') + 1);
+      const HostMesh* hm = nullptr;
+      for (auto& x : m.meshes) if (x.name == mn) hm = &x;
+      if (!hm) return -1;
+      tmp = k.rfind("hull_adjadr:", 0) == 0 ? hm->adjadr : k.rfind("hull_adj:", 0) == 0 ? hm->adj : hm->hull_faces;
+    } else return -1;
+    v = &tmp;
+  }
+  if (!out) return (int64_t)v->size();
+  int64_t nw = std::min<int64_t>(cap, (int64_t)v->size());
+  for (int64_t i = 0; i < nw; i++) out[i] = (*v)[i];
+  return nw;
+}
+
+/* names of bodies / geoms / meshes / cameras, '\n'-separated; returns the length needed */
+extern "C" int64_t grs_model_names(const grs_sim* s, const char* kind, char* out, int64_t cap) {
+  if (!s || !kind) return -1;
+  std::string k = kind, r;
+  const std::vector<std::string>* v = nullptr;
+  std::vector<std::string> tmp;
+  if (k == "body") v = &s->hm.body_names;
+  else if (k == "geom") v = &s->hm.geom_names;
+  else if (k == "joint") v = &s->hm.jnt_names;
+  else if (k == "camera") v = &s->hm.cam_names;
+  else if (k == "mesh") { for (auto& m : s->hm.meshes) tmp.push_back(m.name); v = &tmp; }
+  else return -1;
+  for (size_t i = 0; i < v->size(); i++) { if (i) r += "\n"; r += (*v)[i]; }
+  if (out && cap > 0) { size_t nw = std::min<size_t>((size_t)cap - 1, r.size()); std::memcpy(out, r.data(), nw); out[nw] = 0; }
+  return (int64_t)r.size() + 1;
+}
+
+extern "C" int32_t grs_render(grs_sim* s, int32_t camera_id, int32_t width, int32_t height, uint8_t* rgb_dev, float* depth_dev, void* stream) {
+  GUARD(s);
+  if (camera_id < 0 || camera_id >= s->hm.ncam) return fail("camera_id out of range");
+  if (width <= 0 || height <= 0 || width * height > 640 * 480) return fail("render size out of range");
+  try {
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    launch_queue_kernel_prep(s, st);
+    k_camera_state<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, camera_id);
+    CU(cudaGetLastError());
+    launch_render_raw(s->scene, s->b.debug, DEBUG_STRIDE, rgb_dev, depth_dev, s->n, height, width, s->hm.cam_fovy[camera_id], st);
+    s->launches += 2;
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" uint64_t grs_launch_count(const grs_sim* s) { return s ? s->launches : 0; }
+
+extern "C" float grs_step_kernel_ms(grs_sim* s, int32_t reset_counters) {
+  if (!s || s->compile_only) return 0.0f;
+  cudaSetDevice(s->device);
+  harvest_events(s);
+  float avg = s->ms_cnt ? (float)(s->ms_sum / s->ms_cnt) : 0.0f;
+  if (reset_counters) { s->ms_sum = 0; s->ms_cnt = 0; }
+  return avg;
+}

@@ -66,7 +66,7 @@ HostModel compile_mjcf(const std::string& xml_path);
 
 // ---------------------------------------------------------------- device model (fp32 POD)
 struct DevModel {
-  int nbody, njnt, ngeom, npair, nlevel, nhv_total, pad0, pad1;
+  int nbody, njnt, ngeom, npair, nlevel, nhv_total, iterations, ncam;
   float timestep, impratio, meaninertia, solver_scale;
   float gravity[3], xfrc_ee_z;  // xfrc_ee_z = 0.438*9.81, robot_env.py:64-65
   // bodies, stored in level order is NOT assumed: level_body lists body ids per depth level
@@ -96,6 +96,13 @@ struct DevModel {
   int act_dof[NU + 1];
   float act_gear[NU + 1], act_lo[NU + 1], act_hi[NU + 1];
   int body_ee, body_object, finger1[2], finger2[2], pad2, pad3;
+  // cameras (fixed, or targetbodycom: look at the subtree CoM of a body)
+  int cam_body[MAXCAM], cam_mode[MAXCAM], cam_target[MAXCAM];
+  float cam_pos[MAXCAM][3], cam_quat[MAXCAM][4], cam_fovy[MAXCAM];
 };
+
+// Flatten a HostModel into the device layout.  hull vertices (float4, w = 0) and the per-geom hull graph
+// ([nvert+1 offsets][neighbours], one block per geom) go to separate arrays.
+void build_dev_model(const HostModel& h, DevModel& d, std::vector<float>& hull_verts4, std::vector<int>& hull_adj);
 
 }  // namespace grs

@@ -41,6 +41,8 @@ struct __align__(16) WS {
   float e_D[MAXEFC], e_aref[MAXEFC], e_jar[MAXEFC], e_Jv[MAXEFC], e_force[MAXEFC], e_act[MAXEFC];
   float hc[MAXCON][16];
   int istate[32];
+  // environment layer (env_kernels.cuh): controller targets and the staged per-step record
+  float tgt[8], init_q[8], out[32];
   union {
     struct {  // smooth-dynamics scratch (dead once qfrc_bias is known)
       float xipos[MAXB][3], ximat[MAXB][9], cinert[MAXB][10], crb[MAXB][10], cdofdot[16][6], cvel[MAXB][6], cfrc[MAXB][6];
@@ -1030,10 +1032,10 @@ __device__ __noinline__ void euler_integrate(const DevModel& m, WS& w, int lane)
 }
 
 // dm_control Physics.step() in legacy mode: mj_step2 on the already-computed position stage, then mj_step1.
-__device__ __forceinline__ int physics_step(const DevModel& m, WS& w, const float4* hv, const int* adj, int lane, float xfrc_z, bool actuation = true) {
+__device__ __noinline__ int physics_step(const DevModel& m, WS& w, const float4* hv, const int* adj, int lane, float xfrc_z, bool actuation) {
   smooth_forces(m, w, lane, actuation, xfrc_z);
   make_constraint(m, w, lane);
-  int it = solve_newton(m, w, lane, 50);
+  int it = solve_newton(m, w, lane, m.iterations);
   euler_integrate(m, w, lane);
   forward_position(m, w, hv, adj, lane);
   return it;

@@ -1,0 +1,273 @@
+"""BatchedRobotVecEnv — drop-in for `DummyVecEnv([lambda: Monitor(RobotEnv(config))])` (reference train_agent.py:17-23)
+holding thousands of RobotEnv instances on one GPU.
+
+Follows the stable-baselines3 VecEnv protocol (reset / step_async / step_wait / step, auto-reset with
+infos[i]["terminal_observation"], "TimeLimit.truncated", Monitor's infos[i]["episode"], get_attr / set_attr /
+env_method / env_is_wrapped / seed / close).  stable-baselines3 and gym are not importable in the build image, so the
+class subclasses SB3's VecEnv only when it is present and otherwise duck-types the same methods; spaces fall back to
+small stand-ins with the attributes SB3 reads (shape, dtype, low, high, spaces).
+
+`infos` is a lazy sequence: a 4 096-element list of 16-key dicts per step would dominate the wall time
+(SURVEY.md §8b), so the per-env dict (same keys as robot_env.py:226-241) is built on first access.
+"""
+import time
+from collections.abc import Sequence
+
+import numpy as np
+
+from ._native import INFO
+from .config import make_config
+from .sim import GripperSim
+
+try:  # pragma: no cover - not installed in the build image
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+except Exception:  # noqa: BLE001
+    _VecEnvBase = object
+
+try:  # pragma: no cover
+    from gym import spaces as _spaces
+except Exception:  # noqa: BLE001
+    try:
+        from gymnasium import spaces as _spaces
+    except Exception:  # noqa: BLE001
+        _spaces = None
+
+
+class _Box:
+    def __init__(self, low, high, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.low = np.full(self.shape, low, dtype=self.dtype)
+        self.high = np.full(self.shape, high, dtype=self.dtype)
+
+    def sample(self):
+        if self.dtype == np.uint8:
+            return np.random.randint(0, 256, self.shape).astype(np.uint8)
+        return np.random.uniform(-1, 1, self.shape).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+
+class _Dict(dict):
+    def __init__(self, spaces):
+        super().__init__(spaces)
+        self.spaces = spaces
+
+
+def _box(low, high, shape, dtype):
+    if _spaces is not None:
+        return _spaces.Box(low=low, high=high, shape=shape, dtype=dtype)
+    return _Box(low, high, shape, dtype)
+
+
+def make_spaces(config):
+    """sensor.py:12-54 (observation) and actuator.py:217-247 (action)."""
+    c = 5 if config.full_observation else 4
+    d = {"observation": _box(0, 255, (c, config.height_capture, config.width_capture), np.uint8),
+         "achieved_goal": _box(-np.inf, np.inf, (2,), np.float32),
+         "desired_goal": _box(-np.inf, np.inf, (2,), np.float32)}
+    obs = _spaces.Dict(d) if _spaces is not None else _Dict(d)
+    act = _box(-1.0, 1.0, (6 if config.include_roll else 5,), np.float32)
+    return obs, act
+
+
+STATUS_NAMES = ("RUNNING", "FAIL", "TIME_LIMIT")  # RobotEnv.Status, robot_env.py:19-22
+
+
+class LazyInfos(Sequence):
+    """infos of one vectorised step; infos[i] is built on demand from the packed info rows."""
+
+    def __init__(self, rows, dones, terminal_obs, target_dir, t_start, extra=None):
+        self._rows, self._dones, self._tobs, self._dir, self._t0 = rows, dones, terminal_obs, target_dir, t_start
+        self._cache = {}
+        self._extra = extra or {}
+
+    def __len__(self):
+        return len(self._rows)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if i in self._cache:
+            return self._cache[i]
+        r = self._rows[i]
+        I = INFO
+        status = int(r[I["STATUS"]])
+        d = {"init_obj_pos": r[I["INIT_OBJ_POS"]:I["INIT_OBJ_POS"] + 3].astype(np.float64),
+             "final_obj_pos": r[I["FINAL_OBJ_POS"]:I["FINAL_OBJ_POS"] + 3].astype(np.float64),
+             "target_dir": self._dir,
+             "gripper_open": bool(r[I["GRIPPER_OPEN"]]),
+             "controls": np.zeros(2),  # ctrl[5:7] is always zero when step() returns (robot_env.py:149,168)
+             "object_grasped": int(r[I["OBJECT_GRASPED"]]),
+             "episode_step": int(r[I["EPISODE_STEP"]]),
+             "status": STATUS_NAMES[status],
+             "gripper_position": r[I["GRIPPER_POS"]:I["GRIPPER_POS"] + 3].astype(np.float64),
+             "object_position": r[I["FINAL_OBJ_POS"]:I["FINAL_OBJ_POS"] + 3].astype(np.float64),
+             "position_reached": {"target": bool(r[I["REACHED_TARGET"]]), "initial": bool(r[I["REACHED_INITIAL"]]), "fail": bool(r[I["FAIL"]])},
+             "total_distance": float(r[I["TOTAL_DISTANCE"]]),
+             "line_distance": float(r[I["LINE_DISTANCE"]]),
+             "substeps": int(r[I["NSUB_A"]] + r[I["NSUB_B"]] + r[I["NSUB_C"]]),
+             "achieved_goal": r[I["ACHIEVED"]:I["ACHIEVED"] + 2].copy(),
+             "desired_goal": r[I["DESIRED"]:I["DESIRED"] + 2].copy()}
+        if self._dones[i]:
+            d["TimeLimit.truncated"] = status == 2
+            if self._tobs is not None:
+                d["terminal_observation"] = {"observation": self._tobs[i], "achieved_goal": d["achieved_goal"], "desired_goal": d["desired_goal"]}
+            d["episode"] = {"r": float(r[I["EPISODE_RETURN"]]), "l": int(r[I["EPISODE_STEP"]]), "t": round(time.time() - self._t0, 6)}
+        for k, v in self._extra.items():
+            d[k] = v[i]
+        self._cache[i] = d
+        return d
+
+
+class BatchedRobotVecEnv(_VecEnvBase):
+    """VecEnv of `num_envs` RobotEnv instances (reference simulation/environment/robot_env.py) on one GPU."""
+
+    metadata = {"render.modes": ["rgb_array", "depth_array"]}
+
+    def __init__(self, config=None, num_envs=1, device=0, **overrides):
+        if config is None:
+            config = make_config(**overrides)
+        self.config = config
+        self.sim = GripperSim(config, num_envs=num_envs, device=device, auto_reset=True)
+        self.observation_space, self.action_space = make_spaces(config)
+        if _VecEnvBase is not object:  # pragma: no cover
+            super().__init__(num_envs, self.observation_space, self.action_space)
+        self.num_envs = int(num_envs)
+        self.target_direction = np.array([1, 1]) if config.direction == 45 else np.array([1, 0])  # robot_env.py:30-33
+        self._t_start = time.time()
+        self._actions = None
+        import torch
+        N, (C, H, W) = self.num_envs, self.sim.obs_shape
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+        self._h_act = pin((N, self.sim.action_dim), torch.float32)
+        self._h_obs = pin((N, C, H, W), torch.uint8)
+        self._h_tobs = pin((N, C, H, W), torch.uint8)
+        self._h_ag, self._h_dg = pin((N, 2), torch.float32), pin((N, 2), torch.float32)
+        self._h_rew, self._h_done = pin((N,), torch.float32), pin((N,), torch.uint8)
+        self._h_info = pin((N, INFO["STRIDE"]), torch.float32)
+
+    # ------------------------------------------------------------------ VecEnv protocol
+    def reset(self):
+        self.sim.reset_host(self._h_obs, self._h_ag, self._h_dg)
+        return self._obs_dict()
+
+    def step_async(self, actions):
+        a = np.asarray(actions, dtype=np.float32)
+        if a.shape != self._h_act.shape:
+            raise ValueError("actions must have shape %s, got %s" % (self._h_act.shape, a.shape))
+        self._h_act[...] = np.clip(a, -1.0, 1.0)
+        self._actions = self._h_act
+
+    def step_wait(self):
+        if self._actions is None:
+            raise RuntimeError("step_wait() called without step_async()")
+        self.sim.step_host(self._actions, self._h_obs, self._h_ag, self._h_dg, self._h_rew, self._h_done, self._h_info, self._h_tobs)
+        self._actions = None
+        dones = self._h_done.astype(bool)
+        infos = LazyInfos(self._h_info.copy(), dones, self._h_tobs.copy() if dones.any() else None, self.target_direction, self._t_start)
+        return self._obs_dict(), self._h_rew.copy(), dones, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def _obs_dict(self):
+        return {"observation": self._h_obs.copy(), "achieved_goal": self._h_ag.copy(), "desired_goal": self._h_dg.copy()}
+
+    # zero-copy device path (rollouts that keep the policy on the GPU): tensors alias the simulator's buffers
+    def step_tensors(self, actions):
+        self.sim.step(actions)
+        s = self.sim
+        return {"observation": s.obs, "achieved_goal": s.achieved_goal, "desired_goal": s.desired_goal}, s.reward, s.done, s.info
+
+    def close(self):
+        self.sim.close()
+
+    def seed(self, seed=None):
+        # the reference creates np_random but never consumes it (robot_env.py:28,46): resets are deterministic
+        return [seed] * self.num_envs
+
+    def get_attr(self, attr_name, indices=None):
+        n = len(self._indices(indices))
+        if attr_name in ("target_direction",):
+            return [self.target_direction] * n
+        if attr_name == "config":
+            return [self.config] * n
+        if attr_name in ("episode_step", "gripper_open", "status"):
+            f = self.sim.get_state()["flags"]
+            col = {"gripper_open": 0, "episode_step": 1, "status": 2}[attr_name]
+            vals = f[self._indices(indices), col]
+            if attr_name == "gripper_open":
+                return [bool(v) for v in vals]
+            if attr_name == "status":
+                return [STATUS_NAMES[int(v)] for v in vals]
+            return [int(v) for v in vals]
+        if hasattr(self, attr_name):
+            return [getattr(self, attr_name)] * n
+        raise AttributeError(attr_name)
+
+    def set_attr(self, attr_name, value, indices=None):
+        raise AttributeError("environment attributes are fixed at construction (scene, direction and config are compiled into the simulator)")
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        idx = self._indices(indices)
+        if method_name == "compute_reward":
+            r = self.compute_reward(*method_args, **method_kwargs)
+            return [r] if np.ndim(r) == 0 else list(np.atleast_1d(r))
+        if method_name == "seed":
+            return [None] * len(idx)
+        raise AttributeError("env_method(%r) is not supported by the batched environment" % method_name)
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * len(self._indices(indices))
+
+    def _indices(self, indices):
+        if indices is None:
+            return list(range(self.num_envs))
+        if isinstance(indices, int):
+            return [indices]
+        return list(indices)
+
+    def get_images(self):
+        rgb, _ = self.sim.render(camera_id=2, width=self.config.width_capture, height=self.config.height_capture)
+        return list(rgb.cpu().numpy())
+
+    def render(self, mode="rgb_array", camera_id=None, width=640, height=480, env_index=0):
+        """RobotEnv.render (robot_env.py:302-340): camera_id 0-2 = one camera, 3 = cameras 0-2 side by side."""
+        cid = self.config.camera_id if camera_id is None else camera_id
+        cams = [cid] if cid in (0, 1, 2) else list(range(cid))
+        out = []
+        for c in cams:
+            rgb, depth = self.sim.render(camera_id=c, width=width, height=height)
+            out.append((depth if mode == "depth_array" else rgb)[env_index].cpu().numpy())
+        return np.hstack(out)
+
+    # ------------------------------------------------------------------ HER support
+    def compute_reward(self, achieved_goal, desired_goal, info):
+        """RobotEnv.compute_reward (robot_env.py:243-273) for stored transitions: progress reward from the recorded
+        object positions (+ the HER goal term).  `info` may be one dict or a sequence/array of dicts."""
+        infos = [info] if isinstance(info, dict) else list(info)
+        ag = np.atleast_2d(np.asarray(achieved_goal, dtype=np.float32))
+        dg = np.atleast_2d(np.asarray(desired_goal, dtype=np.float32))
+        out = np.zeros(len(infos), np.float64)
+        d = self.target_direction.astype(np.float64)
+        for k, inf in enumerate(infos):
+            ip, fp = np.asarray(inf["init_obj_pos"], np.float64), np.asarray(inf["final_obj_pos"], np.float64)
+            pi, pf = ip[:2] @ d / (d @ d), fp[:2] @ d / (d @ d)
+            lat, trav = np.linalg.norm(pf * d - fp[:2]), pf - pi
+            r = 0.0
+            if 0.0 < trav < 0.1 and lat < 0.1:
+                r = trav
+                ctr = np.asarray(inf.get("controls", (0.0, 0.0)))
+                if (not inf["gripper_open"]) and bool(np.all(ctr) != 0) and inf["object_grasped"] == 3:
+                    r *= 2
+                    if fp[2] > 0:
+                        r *= 1.5
+            out[k] = r * 30
+            if self.config.her_buffer:
+                out[k] += 1.0 / np.exp(np.linalg.norm(dg[min(k, len(dg) - 1)] - ag[min(k, len(ag) - 1)]))
+        return out if not isinstance(info, dict) else float(out[0])
