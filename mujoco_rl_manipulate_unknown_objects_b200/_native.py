@@ -33,8 +33,10 @@ SYMBOLS = ["grs_last_error", "grs_default_config", "grs_create", "grs_destroy", 
            "grs_obs_shape", "grs_stream", "grs_reset", "grs_step", "grs_step_host", "grs_reset_host", "grs_substep",
            "grs_buffer", "grs_get_state", "grs_set_state", "grs_max_contacts", "grs_get_contacts", "grs_debug_step",
            "grs_model_get", "grs_model_get_int", "grs_model_names", "grs_compile_only", "grs_render", "grs_launch_count",
-           "grs_step_kernel_ms",
-           "grp_create", "grp_destroy", "grp_num_params", "grp_set_params", "grp_get_params", "grp_forward", "grp_last_error"]
+           "grs_step_kernel_ms"]
+POLICY_SYMBOLS = ["grp_create", "grp_destroy", "grp_num_params", "grp_set_params", "grp_get_params", "grp_forward", "grp_last_error"]
+if os.path.exists(os.path.join(HERE, "csrc", "policy_kernels.cu")):
+    SYMBOLS = SYMBOLS + POLICY_SYMBOLS
 
 _lib = None
 

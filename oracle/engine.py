@@ -165,6 +165,33 @@ class Model:
             pass
 
 
+def model_dict_from_export(cm):
+    """Model dict (mjModel-named arrays) from any object with .get(name) / .names(kind) / .sizes — in practice the
+    PRODUCT compiler's export (grs_model_get), so that this engine integrates exactly the model the CUDA kernels
+    integrate (same principal frames, same hull-vertex numbering).  The product compiler itself is checked against
+    oracle/mjcf.py in tests/test_model_compiler.py."""
+    sz = cm.sizes
+    md = {k: sz[k] for k in ("nbody", "njnt", "nq", "nv", "nu", "ngeom", "nmesh")}
+    md["iterations"] = int(cm.get("iterations")[0])
+    md["cone_elliptic"] = int(cm.get("cone_elliptic")[0])
+    for k in ("timestep", "impratio", "tolerance"):
+        md[k] = float(cm.get(k)[0])
+    md["gravity"] = cm.get("gravity")
+    for k in _D_FIELDS:
+        md[k] = cm.get(k)
+    for k in _I_FIELDS:
+        md[k] = cm.get(k)
+    md["body_names"] = cm.names("body")
+    md["geom_names"] = cm.names("geom")
+    meshes = []
+    for n in cm.names("mesh"):
+        hv = cm.get("hull_verts:" + n).reshape(-1, 3)
+        adr, adj = cm.get("hull_adjadr:" + n), cm.get("hull_adj:" + n)
+        meshes.append(dict(hull_verts=hv, hull_adj=[adj[adr[i]:adr[i + 1]].tolist() for i in range(len(hv))]))
+    md["meshes"] = meshes
+    return md
+
+
 def _view(arr, n, shape=None):
     a = np.ctypeslib.as_array(arr)[:n]
     return a.reshape(shape) if shape else a
