@@ -75,6 +75,11 @@ void build_dev_model(const HostModel& h, DevModel& d, std::vector<float>& hv4, s
     d.dof_ancmask[i] = am;
     d.dof_armature[i] = (float)h.dof_armature[i]; d.dof_damping[i] = (float)h.dof_damping[i]; d.dof_invweight0[i] = (float)h.dof_invweight0[i];
   }
+  // the fused Cholesky (sim_kernels.cuh chol_factor_solve<true>) relies on M being block diagonal with blocks [0,7) and [7,13)
+  for (int i = 0; i < NV; i++) {
+    unsigned blk = i < 7 ? 0x7fu : (0x3fu << 7);
+    if (d.dof_ancmask[i] & ~blk) throw std::runtime_error("dof tree layout is not 7 gripper dofs followed by 6 free-object dofs");
+  }
   hv4.clear(); adj.clear();
   for (int g = 0; g < h.ngeom; g++) {
     d.geom_type[g] = h.geom_type[g]; d.geom_body[g] = h.geom_bodyid[g];

@@ -199,6 +199,61 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// robot_env.py:170-241 — everything after the substep loops: failure checks, goals, observation scalars, reward, done,
+// info record (into w.out).  Shared by the sequential and the lock-step step kernels.
+struct StepCounters { int nsa, nsb, nsc, iters, nconmax, flags, fail, object_grasped; bool reached_target, reached_initial; float tq_rec; };
+
+__device__ __noinline__ void env_finalize(const DevModel& m, const EnvCfg& c, WS& w, EnvFlags& f, const float* init_obj, StepCounters& k, int lane) {
+  int nsa = k.nsa, nsb = k.nsb, nsc = k.nsc, iters = k.iters, nconmax = k.nconmax, flags = k.flags, fail = k.fail, object_grasped = k.object_grasped;
+  const bool reached_target = k.reached_target, reached_initial = k.reached_initial;
+  const float tq_rec = k.tq_rec;
+  // NaN / Inf guard (MuJoCo's mj_checkAcc resets the data; here the episode ends as a FAIL and the env is reset)
+  float chk = 0;
+  if (lane < NQ) chk = w.qpos[lane];
+  if (lane >= 16 && lane - 16 < NV) chk = w.qvel[lane - 16];
+  bool bad = __any_sync(FULL, !isfinite(chk));
+  if (bad) { flags |= 2; f.status = 1; fail = 1; }
+  const float* fo = w.xpos[m.body_object];
+  const float* fg = w.xpos[m.body_ee];
+  float ddx = fo[0] - fg[0], ddy = fo[1] - fg[1];
+  if (sqrtf(ddx * ddx + ddy * ddy) > 1.0f) f.status = 1;
+  float pr = project_dir(fo, c.dir);
+  float desired[2] = {pr * c.dir[0], pr * c.dir[1]}, achieved[2] = {fo[0], fo[1]};
+  int grasp = check_grasp(m, w), pher = pheromone_level(m, w, c.dir);
+  float reward = agent_reward(init_obj, fo, c.dir, f.gripper_open, w.ctrl[5], w.ctrl[6], object_grasped);
+  if (c.her_buffer) {
+    float gx = desired[0] - achieved[0], gy = desired[1] - achieved[1];
+    reward += 1.0f / expf(sqrtf(gx * gx + gy * gy));
+  }
+  if (bad) reward = 0;
+  int done;
+  if (f.status != 0) done = 1;
+  else if (f.episode_step == c.time_horizon - 1) { done = 1; f.status = 2; }
+  else done = 0;
+  float tdx = fo[0] - init_obj[0], tdy = fo[1] - init_obj[1];
+  float ip = project_dir(init_obj, c.dir), ldx = pr * c.dir[0] - fo[0], ldy = pr * c.dir[1] - fo[1];
+  float lat = sqrtf(ldx * ldx + ldy * ldy), trav = pr - ip;
+  f.episode_step++;
+  f.ep_return += reward;
+  f.ep_substeps += (float)(nsa + nsb + nsc);
+  __syncwarp();
+  if (lane == 0) {
+    float* o = w.out;
+    o[IN_REWARD] = reward; o[IN_DONE] = (float)done; o[IN_STATUS] = (float)f.status; o[IN_GRASP] = (float)grasp; o[IN_PHEROMONE] = (float)pher;
+    o[IN_OBJECT_GRASPED] = (float)object_grasped; o[IN_GRIPPER_OPEN] = (float)f.gripper_open; o[IN_REACHED_TARGET] = reached_target;
+    o[IN_REACHED_INITIAL] = reached_initial; o[IN_FAIL] = (float)fail; o[IN_NSUB_A] = (float)nsa; o[IN_NSUB_B] = (float)nsb; o[IN_NSUB_C] = (float)nsc;
+    o[IN_TOTAL_DISTANCE] = sqrtf(tdx * tdx + tdy * tdy);
+    o[IN_LINE_DISTANCE] = (trav > 0.f && trav < 0.1f && lat < 0.1f) ? trav : 0.f;
+    for (int k = 0; k < 3; k++) { o[IN_INIT_OBJ_POS + k] = init_obj[k]; o[IN_FINAL_OBJ_POS + k] = fo[k]; o[IN_GRIPPER_POS + k] = fg[k]; }
+    o[IN_ACHIEVED] = achieved[0]; o[IN_ACHIEVED + 1] = achieved[1]; o[IN_DESIRED] = desired[0]; o[IN_DESIRED + 1] = desired[1];
+    o[IN_SOLVER_ITERS] = (float)iters; o[IN_NCON_MAX] = (float)nconmax; o[IN_FLAGS] = (float)flags; o[IN_EPISODE_STEP] = (float)f.episode_step;
+    o[IN_EPISODE_RETURN] = f.ep_return; o[IN_EPISODE_SUBSTEPS] = f.ep_substeps;
+  }
+  if (lane < 5) w.out[IN_TARGET_QPOS + lane] = tq_rec;
+  if (lane >= 5 && lane < 6) w.out[IN_TARGET_QPOS + 5] = 0;
+  __syncwarp();
+}
+
 // robot_env.py:77-241 — one agent step of one environment, executed by one warp.  `act` is the raw action row.
 // Writes the info record into w.out (IN_* layout) and updates f.
 __device__ __noinline__ void env_step(const DevModel& m, const EnvCfg& c, WS& w, EnvFlags& f, const float4* hv, const int* adj, const float* __restrict__ act, int lane) {
@@ -290,51 +345,10 @@ __device__ __noinline__ void env_step(const DevModel& m, const EnvCfg& c, WS& w,
     }
     __syncwarp();
   }
-  // NaN / Inf guard (MuJoCo's mj_checkAcc resets the data; here the episode ends as a FAIL and the env is reset)
-  float chk = 0;
-  if (lane < NQ) chk = w.qpos[lane];
-  if (lane >= 16 && lane - 16 < NV) chk = w.qvel[lane - 16];
-  bool bad = __any_sync(FULL, !isfinite(chk));
-  if (bad) { flags |= 2; f.status = 1; fail = 1; }
-  const float* fo = w.xpos[m.body_object];
-  const float* fg = w.xpos[m.body_ee];
-  float ddx = fo[0] - fg[0], ddy = fo[1] - fg[1];
-  if (sqrtf(ddx * ddx + ddy * ddy) > 1.0f) f.status = 1;
-  float pr = project_dir(fo, c.dir);
-  float desired[2] = {pr * c.dir[0], pr * c.dir[1]}, achieved[2] = {fo[0], fo[1]};
-  int grasp = check_grasp(m, w), pher = pheromone_level(m, w, c.dir);
-  float reward = agent_reward(init_obj, fo, c.dir, f.gripper_open, w.ctrl[5], w.ctrl[6], object_grasped);
-  if (c.her_buffer) {
-    float gx = desired[0] - achieved[0], gy = desired[1] - achieved[1];
-    reward += 1.0f / expf(sqrtf(gx * gx + gy * gy));
-  }
-  if (bad) reward = 0;
-  int done;
-  if (f.status != 0) done = 1;
-  else if (f.episode_step == c.time_horizon - 1) { done = 1; f.status = 2; }
-  else done = 0;
-  float tdx = fo[0] - init_obj[0], tdy = fo[1] - init_obj[1];
-  float ip = project_dir(init_obj, c.dir), ldx = pr * c.dir[0] - fo[0], ldy = pr * c.dir[1] - fo[1];
-  float lat = sqrtf(ldx * ldx + ldy * ldy), trav = pr - ip;
-  f.episode_step++;
-  f.ep_return += reward;
-  f.ep_substeps += (float)(nsa + nsb + nsc);
-  __syncwarp();
-  if (lane == 0) {
-    float* o = w.out;
-    o[IN_REWARD] = reward; o[IN_DONE] = (float)done; o[IN_STATUS] = (float)f.status; o[IN_GRASP] = (float)grasp; o[IN_PHEROMONE] = (float)pher;
-    o[IN_OBJECT_GRASPED] = (float)object_grasped; o[IN_GRIPPER_OPEN] = (float)f.gripper_open; o[IN_REACHED_TARGET] = reached_target;
-    o[IN_REACHED_INITIAL] = reached_initial; o[IN_FAIL] = (float)fail; o[IN_NSUB_A] = (float)nsa; o[IN_NSUB_B] = (float)nsb; o[IN_NSUB_C] = (float)nsc;
-    o[IN_TOTAL_DISTANCE] = sqrtf(tdx * tdx + tdy * tdy);
-    o[IN_LINE_DISTANCE] = (trav > 0.f && trav < 0.1f && lat < 0.1f) ? trav : 0.f;
-    for (int k = 0; k < 3; k++) { o[IN_INIT_OBJ_POS + k] = init_obj[k]; o[IN_FINAL_OBJ_POS + k] = fo[k]; o[IN_GRIPPER_POS + k] = fg[k]; }
-    o[IN_ACHIEVED] = achieved[0]; o[IN_ACHIEVED + 1] = achieved[1]; o[IN_DESIRED] = desired[0]; o[IN_DESIRED + 1] = desired[1];
-    o[IN_SOLVER_ITERS] = (float)iters; o[IN_NCON_MAX] = (float)nconmax; o[IN_FLAGS] = (float)flags; o[IN_EPISODE_STEP] = (float)f.episode_step;
-    o[IN_EPISODE_RETURN] = f.ep_return; o[IN_EPISODE_SUBSTEPS] = f.ep_substeps;
-  }
-  if (lane < 5) w.out[IN_TARGET_QPOS + lane] = tq_rec;
-  if (lane >= 5 && lane < 6) w.out[IN_TARGET_QPOS + 5] = 0;
-  __syncwarp();
+  StepCounters k;
+  k.nsa = nsa; k.nsb = nsb; k.nsc = nsc; k.iters = iters; k.nconmax = nconmax; k.flags = flags; k.fail = fail; k.object_grasped = object_grasped;
+  k.reached_target = reached_target; k.reached_initial = reached_initial; k.tq_rec = tq_rec;
+  env_finalize(m, c, w, f, init_obj, k, lane);
 }
 
 // ----------------------------------------------------------------------------------------------- kernels
@@ -381,7 +395,7 @@ __device__ __forceinline__ int next_env(int* queue, int lane) {
 }
 
 // RobotEnv.step for every environment (+ SB3 VecEnv auto-reset when cfg.auto_reset)
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_env_step(SimBuffers s, EnvCfg c, const float* __restrict__ actions, int adim) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) k_env_step(SimBuffers s, EnvCfg c, const float* __restrict__ actions, int adim) {
   const DevModel& m = stage_model(s.model);
   WS& w = my_ws();
   const int lane = threadIdx.x & 31;
@@ -466,7 +480,7 @@ __global__ void k_reset(SimBuffers s, const unsigned char* __restrict__ mask) {
 }
 
 // n x physics.step() with the controls held in the state (parity tests; robot_env.py:100)
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_substep(SimBuffers s, int nsteps) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) k_substep(SimBuffers s, int nsteps) {
   const DevModel& m = stage_model(s.model);
   WS& w = my_ws();
   const int lane = threadIdx.x & 31;

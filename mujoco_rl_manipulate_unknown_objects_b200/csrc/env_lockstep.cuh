@@ -1,0 +1,235 @@
+// Lock-step variant of the fused agent-step kernel.
+//
+// The sequential kernel (k_env_step in env_kernels.cuh) lets every warp run its own environment's state machine
+// freely.  Profiling showed it to be INSTRUCTION-FETCH bound: ~120 KB of hot code per substep, 20 warps per SM at
+// unrelated program counters, 58 % hit rate in the 32 KB SM instruction cache and half of all issue slots lost to
+// "no instruction" stalls (profiles/r1_env_step_sequential.md).  Here all warps of a block walk the substep pipeline
+// TOGETHER — smooth forces | constraint rows | Newton solve | integrate + kinematics | CRB | collision — with a block
+// barrier between the stages, so the SM's instruction cache only ever holds one stage's code.  The per-environment
+// controller state machine (reference robot_env.py:77-241) becomes an explicit `tick` that runs between rounds and
+// decides, per warp, whether this round carries a physics substep; environments still come from the atomic queue, so
+// ragged trip counts only cost idle warps inside a round, never idle rounds.
+#pragma once
+#include "env_kernels.cuh"
+
+namespace grs {
+
+enum Stage { S_IDLE = 0, S_LOADED, S_BEGIN, S_A_PRE, S_A_POST, S_AFTER_A, S_B_PRE, S_B_POST, S_AFTER_B, S_OPEN_PRE, S_OPEN_POST, S_CLOSE_PRE, S_CLOSE_POST, S_FINISH };
+
+struct EnvCtl {
+  int stage, i, step_limit, env;
+  float open_close, deltas, init_obj[3];
+  StepCounters k;
+  EnvFlags f;
+};
+
+__device__ __forceinline__ void ctl_stats(EnvCtl& t, const WS& w, int iters) {
+  t.k.iters += iters;
+  t.k.nconmax = max(t.k.nconmax, w.ncon);
+  t.k.flags |= w.overflow;
+}
+
+// Advances the controller state machine of one environment up to the next physics substep.
+// Returns true when a substep has to be integrated this round (controls are set), false when the agent step is complete
+// (w.out holds the info record, t.f the updated flags).  `solver_iters` = Newton iterations of the substep just taken.
+__device__ __noinline__ bool env_tick(const DevModel& m, const EnvCfg& c, WS& w, EnvCtl& t, const float* __restrict__ act, int solver_iters, int lane) {
+  const float scale = lane < 3 ? 1.0f / c.max_trans : 1.0f / c.max_rot;
+#pragma unroll 1
+  for (;;) {
+    switch (t.stage) {
+      case S_BEGIN: {  // robot_env.py:87-95
+        float a6[6];
+        if (c.include_roll) { for (int k = 0; k < 6; k++) a6[k] = act[k]; }
+        else { a6[0] = act[0]; a6[1] = act[1]; a6[2] = act[2]; a6[3] = 0; a6[4] = act[3]; a6[5] = act[4]; }
+        t.open_close = a6[5];
+        for (int k = 0; k < 3; k++) t.init_obj[k] = w.xpos[m.body_object][k];
+        if (lane < 5) w.init_q[lane] = w.qpos[lane];
+        if (lane == 0) get_target_pose(m, c, w, a6);
+        __syncwarp();
+        t.k.tq_rec = lane < 5 ? w.tgt[lane] : 0.0f;
+        t.k.nsa = t.k.nsb = t.k.nsc = t.k.iters = t.k.flags = t.k.fail = t.k.object_grasped = 0;
+        t.k.nconmax = w.ncon;
+        t.k.reached_target = t.k.reached_initial = false;
+        t.step_limit = c.max_steps;
+        t.i = 0;
+        t.stage = S_A_PRE;
+        break;
+      }
+      case S_A_PRE:  // robot_env.py:97-100
+      case S_B_PRE:  // robot_env.py:116-119
+        if (t.i >= c.max_steps) { t.stage = t.stage == S_A_PRE ? S_AFTER_A : S_AFTER_B; break; }
+        if (lane < 5) w.ctrl[lane] = (w.tgt[lane] - w.qpos[lane]) * scale;
+        __syncwarp();
+        t.i++;
+        t.stage = t.stage == S_A_PRE ? S_A_POST : S_B_POST;
+        return true;
+      case S_A_POST:
+      case S_B_POST: {  // robot_env.py:104-110, 121-128
+        const bool isA = t.stage == S_A_POST;
+        if (isA) { t.k.nsa++; t.step_limit--; } else t.k.nsb++;
+        ctl_stats(t, w, solver_iters);
+        float d = lane < 5 ? fabsf(w.qpos[lane] - w.tgt[lane]) : 0.0f;
+        d = warp_max(d);
+        if (d < c.pos_tol) {
+          if (isA) t.k.reached_target = true; else t.k.reached_initial = true;
+          if (lane < 5) w.ctrl[lane] = 0;
+          __syncwarp();
+          t.stage = isA ? S_AFTER_A : S_AFTER_B;
+        } else if (!(d == d)) {
+          t.stage = isA ? S_AFTER_A : S_AFTER_B;  // non-finite state: bail out, env_finalize turns it into a FAIL
+        } else {
+          t.stage = isA ? S_A_PRE : S_B_PRE;
+        }
+        break;
+      }
+      case S_AFTER_A:  // robot_env.py:112-114
+        if (t.step_limit == 0) {
+          if (lane < 5) w.tgt[lane] = w.init_q[lane];
+          __syncwarp();
+          t.i = 0;
+          t.stage = S_B_PRE;
+        } else {
+          t.stage = S_AFTER_B;
+        }
+        break;
+      case S_AFTER_B:  // robot_env.py:130-136
+        if (!t.k.reached_target && !t.k.reached_initial) { t.k.fail = 1; t.f.status = 1; }
+        t.i = 0;
+        if (t.k.reached_target && t.open_close > 0.f && !t.f.gripper_open) {
+          if (lane == 0) { w.ctrl[5] = 0.5f; w.ctrl[6] = 0.5f; }
+          __syncwarp();
+          t.stage = S_OPEN_PRE;
+        } else if (t.k.reached_target && t.open_close < 0.f && t.f.gripper_open) {
+          if (lane == 0) { w.ctrl[5] = -1.0f; w.ctrl[6] = -1.0f; }
+          __syncwarp();
+          t.stage = S_CLOSE_PRE;
+        } else {
+          t.stage = S_FINISH;
+        }
+        break;
+      case S_OPEN_PRE:   // robot_env.py:139-142
+      case S_CLOSE_PRE:  // robot_env.py:152-157
+        if (t.i >= c.max_steps) {
+          __syncwarp();
+          if (lane == 0) { w.ctrl[5] = 0; w.ctrl[6] = 0; }
+          __syncwarp();
+          t.stage = S_FINISH;
+          break;
+        }
+        if (t.stage == S_OPEN_PRE) {
+          t.deltas = fmaxf(fabsf(0.4f - w.qpos[5]), fabsf(0.4f - w.qpos[6]));
+          t.stage = S_OPEN_POST;
+        } else {
+          t.deltas = fmaxf(fabsf(-0.4f - w.qpos[5]), fabsf(-0.4f - w.qpos[6]));
+          t.k.object_grasped = check_grasp(m, w);
+          t.stage = S_CLOSE_POST;
+        }
+        t.i++;
+        return true;
+      case S_OPEN_POST:
+      case S_CLOSE_POST: {  // robot_env.py:145-149, 160-168
+        t.k.nsc++;
+        ctl_stats(t, w, solver_iters);
+        bool stop;
+        if (t.stage == S_OPEN_POST) {
+          stop = t.deltas < c.grasp_tol || (w.qpos[5] > 0.4f && w.qpos[6] > 0.4f);
+          if (stop) t.f.gripper_open = 1;
+        } else {
+          stop = t.deltas < c.grasp_tol || t.k.object_grasped == 3;
+          if (stop) t.f.gripper_open = 0;
+        }
+        if (stop || !(t.deltas == t.deltas)) {
+          __syncwarp();
+          if (lane == 0) { w.ctrl[5] = 0; w.ctrl[6] = 0; }
+          __syncwarp();
+          t.stage = S_FINISH;
+        } else {
+          t.stage = t.stage == S_OPEN_POST ? S_OPEN_PRE : S_CLOSE_PRE;
+        }
+        break;
+      }
+      case S_FINISH:
+        env_finalize(m, c, w, t.f, t.init_obj, t.k, lane);
+        t.stage = S_IDLE;
+        return false;
+      default:
+        return false;
+    }
+  }
+}
+
+// results of a finished agent step -> HBM (+ SB3 auto-reset); same record layout as the sequential kernel
+__device__ __noinline__ void env_writeback(const DevModel& m, const EnvCfg& c, const SimBuffers& s, WS& w, EnvCtl& t, int lane) {
+  const int env = t.env;
+  float* st = s.state + (size_t)env * ST_STRIDE;
+  for (int k = lane; k < IN_STRIDE; k += 32) s.info[(size_t)env * IN_STRIDE + k] = w.out[k];
+  write_render_state(m, w, c.obs_cam, s.render_state + (size_t)env * RS_STRIDE, lane);
+  const int done = (int)w.out[IN_DONE];
+  if (lane == 0) {
+    s.reward[env] = w.out[IN_REWARD];
+    s.done[env] = (unsigned char)done;
+    s.achieved[2 * env] = w.out[IN_ACHIEVED]; s.achieved[2 * env + 1] = w.out[IN_ACHIEVED + 1];
+    s.desired[2 * env] = w.out[IN_DESIRED]; s.desired[2 * env + 1] = w.out[IN_DESIRED + 1];
+  }
+  if (done && c.auto_reset) {
+    for (int k = lane; k < ST_STRIDE; k += 32) st[k] = s.reset_record[k];
+    if (lane == 0) {
+      s.achieved[2 * env] = s.reset_record[ST_STRIDE + IN_ACHIEVED]; s.achieved[2 * env + 1] = s.reset_record[ST_STRIDE + IN_ACHIEVED + 1];
+      s.desired[2 * env] = s.reset_record[ST_STRIDE + IN_DESIRED]; s.desired[2 * env + 1] = s.reset_record[ST_STRIDE + IN_DESIRED + 1];
+    }
+  } else {
+    store_state(w, t.f, st, lane);
+  }
+  __syncwarp();
+}
+
+constexpr int LS_MAX_THREADS = 640;  // 20 warps: one block per SM (20 x 10.3 KB workspaces + the model in 227 KB of shared memory)
+
+__global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s, EnvCfg c, const float* __restrict__ actions, int adim) {
+  const DevModel& m = stage_model(s.model);
+  WS& w = my_ws();
+  const int lane = threadIdx.x & 31;
+  EnvCtl t;
+  t.stage = S_IDLE; t.env = -1;
+  bool exhausted = false;
+  int iters = 0;
+#pragma unroll 1
+  for (;;) {
+    // ---- controller round: finish / fetch / decide (per warp, no block-wide dependency)
+    bool dyn = false, pos = false;
+    if (t.stage == S_LOADED) t.stage = S_BEGIN;
+    if (t.stage != S_IDLE) {
+      dyn = env_tick(m, c, w, t, actions + (size_t)t.env * adim, iters, lane);
+      if (!dyn) env_writeback(m, c, s, w, t, lane);
+    }
+    if (t.stage == S_IDLE && !exhausted) {
+      int env = next_env(s.queue, lane);
+      if (env < s.n) {
+        t.env = env;
+        load_state(w, t.f, s.state + (size_t)env * ST_STRIDE, lane);
+        t.stage = S_LOADED;
+        pos = true;  // position stage of the loaded state (no dynamics this round)
+      } else {
+        exhausted = true;
+      }
+    }
+    pos = pos || dyn;
+    if (!__syncthreads_or(pos)) break;
+    // ---- the substep pipeline, stage by stage, whole block in step (dm_control legacy step: mj_step2 then mj_step1)
+    if (dyn) smooth_forces(m, w, lane, true, t.f.xfrc_z);
+    __syncthreads();
+    if (dyn) make_constraint(m, w, lane);
+    __syncthreads();
+    iters = 0;
+    if (dyn) iters = solve_newton(m, w, lane, m.iterations);
+    __syncthreads();
+    if (dyn) euler_integrate(m, w, lane);
+    if (pos) kinematics(m, w, lane);
+    __syncthreads();
+    if (pos) com_pos_crb(m, w, lane);
+    __syncthreads();
+    if (pos) collision(m, w, s.hull, s.adj, lane);
+  }
+}
+
+}  // namespace grs

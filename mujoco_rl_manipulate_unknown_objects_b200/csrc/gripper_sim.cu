@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -15,6 +17,7 @@
 
 #include "../../include/b200_gripper_sim.h"
 #include "env_kernels.cuh"
+#include "env_lockstep.cuh"
 #include "render_kernels.cuh"
 
 using namespace grs;
@@ -56,6 +59,9 @@ struct grs_sim {
   long ms_cnt = 0;
   int grid = 0;
   size_t smem = 0;
+  // lock-step step kernel geometry (GRS_STEP_WARPS warps per block; 0 selects the sequential kernel)
+  int ls_warps = 20, ls_grid = 0;
+  size_t ls_smem = 0;
 };
 
 template <class T>
@@ -164,6 +170,15 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     if (per_sm < 1) throw std::runtime_error("step kernel does not fit on this device");
     int want = (num_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     s->grid = std::min(want, per_sm * nsm);
+    if (const char* e = getenv("GRS_STEP_WARPS")) s->ls_warps = std::max(0, std::min(20, atoi(e)));
+    if (s->ls_warps > 0) {
+      s->ls_smem = (sizeof(DevModel) + 15) / 16 * 16 + (size_t)s->ls_warps * sizeof(WS);
+      CU(cudaFuncSetAttribute(k_env_step_ls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
+      int ls_per_sm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, k_env_step_ls, s->ls_warps * 32, s->ls_smem));
+      if (ls_per_sm < 1) throw std::runtime_error("lock-step step kernel does not fit on this device");
+      s->ls_grid = std::min((num_envs + s->ls_warps - 1) / s->ls_warps, ls_per_sm * nsm);
+    }
     for (int i = 0; i < grs_sim::NEV; i++) { CU(cudaEventCreate(&s->ev0[i])); CU(cudaEventCreate(&s->ev1[i])); }
     render_scene_upload(s->hm, s->scene, s->owned);
     // the reset record and the observation of a freshly reset environment (identical for every env and every episode)
@@ -232,7 +247,8 @@ extern "C" int32_t grs_step(grs_sim* s, const float* actions_dev, void* stream) 
     launch_queue_kernel_prep(s, st);
     if (s->ev_n == grs_sim::NEV) harvest_events(s);
     CU(cudaEventRecord(s->ev0[s->ev_n], st));
-    k_env_step<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
+    if (s->ls_warps > 0) k_env_step_ls<<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
+    else k_env_step<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev1[s->ev_n], st));
     s->ev_n++;

@@ -14,7 +14,7 @@
 namespace grs {
 
 constexpr int NQ = 14, NV = 13, NU = 7;
-constexpr int MAXB = 12, MAXJ = 8, MAXG = 8, MAXPAIR = 16, MAXMESH = 6, MAXLEVEL = 6;
+constexpr int MAXB = 10, MAXJ = 8, MAXG = 8, MAXPAIR = 16, MAXMESH = 6, MAXLEVEL = 6;
 constexpr int MAXCAM = 4, MAXLIGHT = 4;
 
 enum GeomType { GEOM_PLANE = 0, GEOM_BOX = 6, GEOM_MESH = 7 };

@@ -32,7 +32,7 @@ struct __align__(16) WS {
   float cdof[16][6];
   float M[NV * NV];
   // contacts
-  int ncon, nefc, nlim, overflow;
+  int ncon, nefc, nlim, overflow, coupled, padi[3];
   float c_dist[MAXCON], c_pos[MAXCON][3], c_frame[MAXCON][9], c_mu[MAXCON], c_fric[MAXCON][3];
   int c_g1[MAXCON], c_g2[MAXCON], c_pair[MAXCON];
   // dof-space vectors
@@ -44,6 +44,7 @@ struct __align__(16) WS {
   // environment layer (env_kernels.cuh): controller targets and the staged per-step record
   float tgt[8], init_q[8], out[40];
   float sup[5][9];  // MPR portal (collision)
+  float cho[16];    // Cholesky right-hand side / solution exchange
   union {
     struct {  // smooth-dynamics scratch (dead once qfrc_bias is known)
       float xipos[MAXB][3], ximat[MAXB][9], cinert[MAXB][10], crb[MAXB][10], cdofdot[16][6], cvel[MAXB][6], cfrc[MAXB][6];
@@ -135,40 +136,78 @@ __device__ __forceinline__ void cross_force(float* r, const float* v, const floa
   cross3(r + 3, v, f + 3);
 }
 
-// 13x13 Cholesky A = L L^T in shared memory (row stride NV, lower triangle in/out), lane = row.  Rolled loops on
-// purpose: the step kernel is instruction-cache bound (DESIGN.md "instruction footprint"), and this is called 3x per substep.
-__device__ __noinline__ void chol13(float* A, int lane) {
-  const bool row = lane < NV;
-#pragma unroll 1
-  for (int j = 0; j < NV; j++) {
-    float inv = 1.0f / sqrtf(fmaxf(A[j * NV + j], 1e-30f));
-    float lij = 0.0f;
-    if (row && lane >= j) { lij = A[lane * NV + j] * inv; A[lane * NV + j] = lij; }
-    __syncwarp();
-#pragma unroll 2
-    for (int k = j + 1; k < NV; k++) {
-      float lkj = A[k * NV + j];
-      if (row && lane >= k) A[lane * NV + k] -= lij * lkj;
+// Fused 13x13 Cholesky factorisation + solve:  x = (L L^T)^-1 b,  A (shared memory, row stride NV, lower triangle read)
+// is overwritten by L.  Lane i keeps row i in registers; column j is exchanged through A's own column in shared memory
+// (one __syncwarp per column, no shuffles).  The right-hand side rides along as an extra matrix row held by an otherwise
+// idle lane, so the forward substitution costs nothing: after the factorisation that lane holds y = L^-1 b.
+// Two shapes:
+//   BLOCKS = false  dense 13x13 (Newton Hessian when a gripper/object contact couples the two kinematic trees)
+//   BLOCKS = true   block diagonal 7x7 (gripper tree, lanes 0-6, rhs lane 13) + 6x6 (free object, lanes 7-12, rhs lane 14),
+//                   both factorised at once: M, M + h*damping, and the Hessian whenever no contact couples the trees.
+template <bool BLOCKS>
+__device__ __noinline__ float chol_factor_solve(float* A, float* tmp, float b, int lane) {
+  constexpr int NB = BLOCKS ? 7 : NV;
+  const bool is_row = lane < NV;
+  const bool is_rhs = BLOCKS ? (lane == 13 || lane == 14) : (lane == NV);
+  const int base = BLOCKS ? (((lane >= 7 && lane < NV) || lane == 14) ? 7 : 0) : 0;
+  const int nb = BLOCKS ? (base ? 6 : 7) : NV;  // rows of this lane's block
+  const int lr = is_rhs ? NB : lane - base;      // local row (the rhs row sits below the block)
+  if (is_row) tmp[lane] = b;
+  __syncwarp();
+  float a[NB];
+#pragma unroll
+  for (int k = 0; k < NB; k++) {
+    a[k] = 0.0f;
+    if (k < nb) {
+      if (is_row && k <= lr) a[k] = A[lane * NV + base + k];
+      else if (is_rhs) a[k] = tmp[base + k];
     }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    if (is_row && lr >= j) A[lane * NV + base + j] = a[j];  // publish the (unscaled) column j
     __syncwarp();
+    const int cj = base + (j < nb ? j : 0);
+    const float djj = A[cj * NV + cj];
+    float rs = rsqrtf(fmaxf(djj, 1e-30f));
+    rs = rs * (1.5f - 0.5f * djj * rs * rs);  // one Newton step: full fp32 accuracy
+    const float t = a[j] * rs * rs;
+    a[j] *= rs;
+#pragma unroll
+    for (int k = j + 1; k < NB; k++) {
+      const int rk = base + (k < nb ? k : 0);
+      a[k] -= t * A[rk * NV + cj];
+    }
   }
-}
-// solve L L^T x = b ; lane i holds b_i and receives x_i
-__device__ __noinline__ float chol_solve13(const float* L, float b, int lane) {
-  const bool row = lane < NV;
-#pragma unroll 1
-  for (int j = 0; j < NV; j++) {
-    float xj = __shfl_sync(FULL, b, j) / L[j * NV + j];
-    if (lane == j) b = xj;
-    else if (row && lane > j) b -= L[lane * NV + j] * xj;
+  __syncwarp();
+  if (is_row) {
+#pragma unroll
+    for (int k = 0; k < NB; k++)
+      if (k <= lr) A[lane * NV + base + k] = a[k];
   }
-#pragma unroll 1
-  for (int j = NV - 1; j >= 0; j--) {
-    float xj = __shfl_sync(FULL, b, j) / L[j * NV + j];
-    if (lane == j) b = xj;
-    else if (lane < j) b -= L[j * NV + lane] * xj;
+  if (is_rhs) {
+#pragma unroll
+    for (int k = 0; k < NB; k++)
+      if (k < nb) tmp[base + k] = a[k];
   }
-  return b;
+  __syncwarp();
+  float y = is_row ? tmp[lane] : 0.0f;
+  // backward substitution L^T x = y, one column per step, x_j broadcast through tmp
+#pragma unroll
+  for (int j = NB - 1; j >= 0; j--) {
+    const bool valid = j < nb;
+    const int gj = base + (valid ? j : 0);
+    const float ljj = A[gj * NV + gj];
+    if (is_row && valid && lr == j) tmp[gj] = __fdividef(y, ljj);
+    __syncwarp();
+    const float xj = tmp[gj];
+    if (is_row && valid) {
+      if (lr == j) y = xj;
+      else if (lr < j) y -= A[gj * NV + lane] * xj;
+    }
+  }
+  __syncwarp();
+  return y;
 }
 
 // -------------------------------------------------------------------------------- position stage
@@ -692,8 +731,7 @@ __device__ __noinline__ void smooth_forces(const DevModel& m, WS& w, int lane, b
   // factor M into the scratch and solve for qacc_smooth
   for (int e = lane; e < NV * NV; e += 32) w.u.dyn.L[e] = w.M[e];
   __syncwarp();
-  chol13(w.u.dyn.L, lane);
-  float a = chol_solve13(w.u.dyn.L, f, lane);
+  float a = chol_factor_solve<true>(w.u.dyn.L, w.cho, f, lane);  // M never couples the gripper tree and the free object
   if (lane < NV) w.asmooth[lane] = a;
   __syncwarp();
 }
@@ -794,7 +832,14 @@ __device__ __noinline__ void make_constraint(const DevModel& m, WS& w, int lane)
     w.e_aref[r + 2] = -B * vel[2];
     w.e_aref[r + 3] = -B * vel[3];
   }
-  if (lane == 0) { w.nefc = nefc; w.nlim = nlim; }
+  // does any contact couple the two kinematic trees (gripper <-> object)?  If not, the Hessian stays block diagonal.
+  bool cpl = false;
+  if (lane < ncon) {
+    int r1 = m.body_root[m.geom_body[w.c_g1[lane]]], r2 = m.body_root[m.geom_body[w.c_g2[lane]]];
+    cpl = r1 != 0 && r2 != 0 && r1 != r2;
+  }
+  cpl = __any_sync(FULL, cpl);
+  if (lane == 0) { w.nefc = nefc; w.nlim = nlim; w.coupled = cpl; }
   __syncwarp();
 }
 
@@ -995,8 +1040,7 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
     if (iter > 0 && improvement < tol) break;
     __syncwarp();
     make_hessian(w, lane);
-    chol13(w.u.con.H, lane);
-    float s = chol_solve13(w.u.con.H, -g, lane);
+    float s = w.coupled ? chol_factor_solve<false>(w.u.con.H, w.cho, -g, lane) : chol_factor_solve<true>(w.u.con.H, w.cho, -g, lane);
     if (lane < NV) w.search[lane] = s;
     __syncwarp();
     float mv = mat13_vec(w.M, w.search, lane);
@@ -1052,9 +1096,8 @@ __device__ __noinline__ void euler_integrate(const DevModel& m, WS& w, int lane)
     w.u.con.H[e] = w.M[e] + (a == b ? h * m.dof_damping[a] : 0.0f);
   }
   __syncwarp();
-  chol13(w.u.con.H, lane);
   float f = lane < NV ? w.fsmooth[lane] + w.fcon[lane] : 0.0f;
-  float qacc = chol_solve13(w.u.con.H, f, lane);
+  float qacc = chol_factor_solve<true>(w.u.con.H, w.cho, f, lane);
   if (lane < NV) {
     w.warm[lane] = w.qacc[lane];
     w.qvel[lane] += h * qacc;
