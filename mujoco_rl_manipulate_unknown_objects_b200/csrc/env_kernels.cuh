@@ -31,6 +31,7 @@ __device__ __forceinline__ void load_state(WS& w, EnvFlags& f, const float* __re
   if (lane < NU) w.ctrl[lane] = st[ST_CTRL + lane];
   f.gripper_open = (int)st[ST_GRIPPER_OPEN]; f.episode_step = (int)st[ST_EPISODE_STEP]; f.status = (int)st[ST_STATUS];
   f.xfrc_z = st[ST_XFRC_Z]; f.ep_return = st[ST_EP_RETURN]; f.ep_substeps = st[ST_EP_SUBSTEPS];
+  for (int k = lane; k < MAXPAIR * 3; k += 32) (&w.sep[0][0])[k] = 0.0f;  // no separating-axis cache for a freshly loaded state
   __syncwarp();
 }
 __device__ __forceinline__ void store_state(const WS& w, const EnvFlags& f, float* __restrict__ st, int lane) {
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(32) k_make_reset_record(SimBuffers s, EnvCfg c
   WS& w = my_ws();
   const int lane = threadIdx.x & 31;
   if (lane < NQ) w.qpos[lane] = m.qpos0[lane];
+  for (int k = lane; k < MAXPAIR * 3; k += 32) (&w.sep[0][0])[k] = 0.0f;
   if (lane < NV) { w.qvel[lane] = 0; w.warm[lane] = 0; }
   if (lane < NU) w.ctrl[lane] = 0;
   __syncwarp();

@@ -183,12 +183,24 @@ __device__ __noinline__ void env_writeback(const DevModel& m, const EnvCfg& c, c
   __syncwarp();
 }
 
+#ifndef LS_BARRIERS
+#define LS_BARRIERS 4
+#endif
 constexpr int LS_MAX_THREADS = 640;  // 20 warps: one block per SM (20 x 10.3 KB workspaces + the model in 227 KB of shared memory)
 
+// TIMING = true: per-stage clock64 bookkeeping (sum over warps vs. per-round block maximum) into s.debug — a development
+// aid behind GRS_STEP_TIMING=1 that quantifies what the block barriers cost; the production instantiation carries none of it.
+template <bool TIMING>
 __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s, EnvCfg c, const float* __restrict__ actions, int adim) {
   const DevModel& m = stage_model(s.model);
   WS& w = my_ws();
   const int lane = threadIdx.x & 31;
+  __shared__ unsigned long long t_sum[8], t_max[8], t_round[8];
+  __shared__ unsigned long long t_rounds;
+  if (TIMING) { if (threadIdx.x < 8) { t_sum[threadIdx.x] = 0; t_max[threadIdx.x] = 0; t_round[threadIdx.x] = 0; } if (threadIdx.x == 0) t_rounds = 0; __syncthreads(); }
+  long long t0 = 0;
+#define LS_T0() if (TIMING) t0 = clock64();
+#define LS_T1(p) if (TIMING) { unsigned long long d_ = (unsigned long long)(clock64() - t0); if (lane == 0) { atomicAdd(&t_sum[p], d_); atomicMax(&t_round[p], d_); } }
   EnvCtl t;
   t.stage = S_IDLE; t.env = -1;
   bool exhausted = false;
@@ -196,6 +208,7 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
 #pragma unroll 1
   for (;;) {
     // ---- controller round: finish / fetch / decide (per warp, no block-wide dependency)
+    LS_T0();
     bool dyn = false, pos = false;
     if (t.stage == S_LOADED) t.stage = S_BEGIN;
     if (t.stage != S_IDLE) {
@@ -214,22 +227,46 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
       }
     }
     pos = pos || dyn;
+    LS_T1(0);
     if (!__syncthreads_or(pos)) break;
+    if (TIMING && threadIdx.x == 0) { for (int p = 0; p < 8; p++) { t_max[p] += t_round[p]; t_round[p] = 0; } t_rounds++; }
     // ---- the substep pipeline, stage by stage, whole block in step (dm_control legacy step: mj_step2 then mj_step1)
+    LS_T0();
     if (dyn) smooth_forces(m, w, lane, true, t.f.xfrc_z);
-    __syncthreads();
+    LS_T1(1);
+    if (LS_BARRIERS >= 6) __syncthreads();
+    LS_T0();
     if (dyn) make_constraint(m, w, lane);
+    LS_T1(2);
     __syncthreads();
     iters = 0;
+    LS_T0();
     if (dyn) iters = solve_newton(m, w, lane, m.iterations);
+    LS_T1(3);
     __syncthreads();
+    LS_T0();
     if (dyn) euler_integrate(m, w, lane);
     if (pos) kinematics(m, w, lane);
-    __syncthreads();
+    LS_T1(4);
+    if (LS_BARRIERS >= 5) __syncthreads();
+    LS_T0();
     if (pos) com_pos_crb(m, w, lane);
+    LS_T1(5);
     __syncthreads();
+    LS_T0();
     if (pos) collision(m, w, s.hull, s.adj, lane);
+    LS_T1(6);
   }
+  if (TIMING) {
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      s.debug[(size_t)blockIdx.x * 32 + threadIdx.x] = (float)t_sum[threadIdx.x] / (float)(blockDim.x >> 5);
+      s.debug[(size_t)blockIdx.x * 32 + 8 + threadIdx.x] = (float)t_max[threadIdx.x];
+    }
+    if (threadIdx.x == 0) s.debug[(size_t)blockIdx.x * 32 + 16] = (float)t_rounds;
+  }
+#undef LS_T0
+#undef LS_T1
 }
 
 }  // namespace grs

@@ -60,7 +60,8 @@ struct grs_sim {
   int grid = 0;
   size_t smem = 0;
   // lock-step step kernel geometry (GRS_STEP_WARPS warps per block; 0 selects the sequential kernel)
-  int ls_warps = 20, ls_grid = 0;
+  int ls_warps = 10, ls_grid = 0;
+  bool ls_timing = false;
   size_t ls_smem = 0;
 };
 
@@ -173,9 +174,11 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     if (const char* e = getenv("GRS_STEP_WARPS")) s->ls_warps = std::max(0, std::min(20, atoi(e)));
     if (s->ls_warps > 0) {
       s->ls_smem = (sizeof(DevModel) + 15) / 16 * 16 + (size_t)s->ls_warps * sizeof(WS);
-      CU(cudaFuncSetAttribute(k_env_step_ls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
+      CU(cudaFuncSetAttribute(k_env_step_ls<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
+      CU(cudaFuncSetAttribute(k_env_step_ls<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
+      s->ls_timing = getenv("GRS_STEP_TIMING") != nullptr;
       int ls_per_sm = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, k_env_step_ls, s->ls_warps * 32, s->ls_smem));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, k_env_step_ls<false>, s->ls_warps * 32, s->ls_smem));
       if (ls_per_sm < 1) throw std::runtime_error("lock-step step kernel does not fit on this device");
       s->ls_grid = std::min((num_envs + s->ls_warps - 1) / s->ls_warps, ls_per_sm * nsm);
     }
@@ -247,7 +250,8 @@ extern "C" int32_t grs_step(grs_sim* s, const float* actions_dev, void* stream) 
     launch_queue_kernel_prep(s, st);
     if (s->ev_n == grs_sim::NEV) harvest_events(s);
     CU(cudaEventRecord(s->ev0[s->ev_n], st));
-    if (s->ls_warps > 0) k_env_step_ls<<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
+    if (s->ls_warps > 0 && s->ls_timing) k_env_step_ls<true><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
+    else if (s->ls_warps > 0) k_env_step_ls<false><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
     else k_env_step<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev1[s->ev_n], st));

@@ -45,6 +45,7 @@ struct __align__(16) WS {
   float tgt[8], init_q[8], out[40];
   float sup[5][9];  // MPR portal (collision)
   float cho[16];    // Cholesky right-hand side / solution exchange
+  float sep[MAXPAIR][3];  // last separating direction found for each convex pair (zero = none); temporal coherence only
   union {
     struct {  // smooth-dynamics scratch (dead once qfrc_bias is known)
       float xipos[MAXB][3], ximat[MAXB][9], cinert[MAXB][10], crb[MAXB][10], cdofdot[16][6], cvel[MAXB][6], cfrc[MAXB][6];
@@ -515,8 +516,9 @@ __device__ __noinline__ bool mpr_penetration(const DevModel& m, WS& w, const flo
   if (dot3(SUPV(0), SUPV(0)) < 1e-12f) { __syncwarp(); if (lane == 0) w.sup[0][0] += 1e-5f; __syncwarp(); }
   for (int k = 0; k < 3; k++) dir[k] = -SUPV(0)[k];
   normalize3(dir);
+  dir_out[0] = dir_out[1] = dir_out[2] = 0;  // on a `false` return: a direction that separates the two shapes, or zero
   support_md(m, w, hv, g1, g2, margin, dir, 1, lane);
-  if (dot3(SUPV(1), dir) < 0) return false;
+  if (dot3(SUPV(1), dir) < 0) { for (int k = 0; k < 3; k++) dir_out[k] = dir[k]; return false; }
   cross3(dir, SUPV(0), SUPV(1));
   if (dot3(dir, dir) < 1e-14f) {
     // origin lies on the segment v0-v1 (findPenetrSegment) or coincides with v1 (findPenetrTouch)
@@ -527,7 +529,7 @@ __device__ __noinline__ bool mpr_penetration(const DevModel& m, WS& w, const flo
   }
   normalize3(dir);
   support_md(m, w, hv, g1, g2, margin, dir, 2, lane);
-  if (dot3(SUPV(2), dir) < 0) return false;
+  if (dot3(SUPV(2), dir) < 0) { for (int k = 0; k < 3; k++) dir_out[k] = dir[k]; return false; }
   for (int k = 0; k < 3; k++) { va[k] = SUPV(1)[k] - SUPV(0)[k]; vb[k] = SUPV(2)[k] - SUPV(0)[k]; }
   cross3(dir, va, vb);
   normalize3(dir);
@@ -538,7 +540,7 @@ __device__ __noinline__ bool mpr_penetration(const DevModel& m, WS& w, const flo
 #pragma unroll 1
   for (int it = 0; it < 100; it++) {
     support_md(m, w, hv, g1, g2, margin, dir, 3, lane);
-    if (dot3(SUPV(3), dir) < 0) return false;
+    if (dot3(SUPV(3), dir) < 0) { for (int k = 0; k < 3; k++) dir_out[k] = dir[k]; return false; }
     bool cont = false;
     cross3(va, SUPV(1), SUPV(3));
     if (dot3(va, SUPV(0)) < -1e-10f) { sup_copy(w, 2, 3, lane); cont = true; }
@@ -557,7 +559,8 @@ __device__ __noinline__ bool mpr_penetration(const DevModel& m, WS& w, const flo
     portal_dir(w, dir);
     if (dot3(dir, SUPV(1)) >= 0) break;
     support_md(m, w, hv, g1, g2, margin, dir, 4, lane);
-    if (dot3(SUPV(4), dir) < 0 || portal_reach_tol(w, dir, tol)) return false;
+    if (dot3(SUPV(4), dir) < 0) { for (int k = 0; k < 3; k++) dir_out[k] = dir[k]; return false; }
+    if (portal_reach_tol(w, dir, tol)) return false;
     expand_portal(w, lane);
   }
 #pragma unroll 1
@@ -644,7 +647,19 @@ __device__ __noinline__ void collision(const DevModel& m, WS& w, const float4* h
       float bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
       if (dot3(dif, dif) > bound * bound) continue;
       float depth, dir[3], pos[3];
-      if (!mpr_penetration(m, w, hv, g1, g2, margin, &depth, dir, pos, lane)) continue;
+      // temporal coherence: a direction that separated the pair in the previous substep usually still does (one support
+      // evaluation instead of a full MPR run).  It proves the origin lies outside the Minkowski difference, which is
+      // exactly when MPR reports no penetration, so the contact set is unchanged.
+      float ca[3] = {w.sep[p][0], w.sep[p][1], w.sep[p][2]};
+      if (ca[0] != 0.0f || ca[1] != 0.0f || ca[2] != 0.0f) {
+        support_md(m, w, hv, g1, g2, margin, ca, 4, lane);
+        if (dot3(SUPV(4), ca) < 0) continue;
+      }
+      bool hit = mpr_penetration(m, w, hv, g1, g2, margin, &depth, dir, pos, lane);
+      __syncwarp();
+      if (lane < 3) w.sep[p][lane] = hit ? 0.0f : dir[lane];
+      __syncwarp();
+      if (!hit) continue;
       add_contact(m, w, p, margin - depth, pos, dir, lane);
     }
   }

@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""Development aid: per-stage cost of the lock-step step kernel (GRS_STEP_TIMING=1): mean warp time vs. what the block
+barrier makes every warp pay (the per-round maximum)."""
+import os, sys
+os.environ["GRS_STEP_TIMING"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from mujoco_rl_manipulate_unknown_objects_b200 import GripperSim, make_config
+N = 4096
+sim = GripperSim(make_config(sim_env="/xmls/acorn_env.xml"), num_envs=N)
+gen = torch.Generator(device="cuda").manual_seed(0)
+for i in range(12):
+    sim.step(torch.rand((N, 6), device="cuda", generator=gen) * 2 - 1)
+torch.cuda.synchronize()
+d = sim.debug.reshape(-1)[: 32 * 296].reshape(296, 32).cpu().numpy()
+names = ["tick", "smooth", "constraint", "solve", "euler+kin", "crb", "collision"]
+mean, mx = d[:, :7].sum(0), d[:, 8:15].sum(0)
+print("rounds per block: mean %.0f" % d[:, 16].mean())
+for n, a, b in zip(names, mean, mx):
+    print("%-12s mean-warp %6.1f%%   block-max %6.1f%%   max/mean %.2f" % (n, 100 * a / mean.sum(), 100 * b / mx.sum(), b / max(a, 1)))
+print("total: sum of per-round maxima / sum of warp means = %.2f" % (mx.sum() / mean.sum()))
