@@ -427,7 +427,7 @@ static const std::vector<double>* model_field(const HostModel& m, const std::str
 #define F(nm) if (k == #nm) return &m.nm;
   F(body_mass) F(body_pos) F(body_quat) F(body_ipos) F(body_iquat) F(body_inertia) F(body_invweight0) F(dof_invweight0) F(dof_armature)
   F(dof_damping) F(geom_pos) F(geom_quat) F(geom_rbound) F(geom_friction) F(geom_margin) F(geom_gap) F(geom_solref) F(geom_solimp) F(geom_rgba) F(geom_size)
-  F(geom_mass) F(qpos0) F(jnt_pos) F(jnt_axis) F(jnt_range) F(act_gear) F(act_ctrlrange) F(cam_pos) F(cam_quat) F(cam_fovy) F(light_pos) F(light_dir)
+  F(geom_mass) F(geom_matprop) F(light_diffuse) F(light_ambient) F(light_specular) F(qpos0) F(jnt_pos) F(jnt_axis) F(jnt_range) F(act_gear) F(act_ctrlrange) F(cam_pos) F(cam_quat) F(cam_fovy) F(light_pos) F(light_dir)
 #undef F
   return nullptr;
 }
@@ -435,7 +435,7 @@ static const std::vector<int>* model_field_int(const HostModel& m, const std::st
 #define F(nm) if (k == #nm) return &m.nm;
   F(body_parentid) F(body_weldid) F(body_jntadr) F(body_jntnum) F(body_dofadr) F(body_dofnum) F(body_rootid) F(jnt_type) F(jnt_bodyid) F(jnt_qposadr)
   F(jnt_dofadr) F(jnt_limited) F(dof_bodyid) F(dof_jntid) F(dof_parentid) F(geom_type) F(geom_bodyid) F(geom_meshid) F(geom_condim) F(act_dofid)
-  F(pair_geom1) F(pair_geom2) F(cam_bodyid) F(cam_mode) F(cam_target)
+  F(pair_geom1) F(pair_geom2) F(cam_bodyid) F(cam_mode) F(cam_target) F(light_bodyid) F(light_directional)
 #undef F
   return nullptr;
 }
@@ -456,8 +456,20 @@ extern "C" int64_t grs_model_get(const grs_sim* s, const char* name, double* out
     else if (k == "gravity") tmp = {m.gravity[0], m.gravity[1], m.gravity[2]};
     else if (k == "znear") tmp = {m.znear};
     else if (k == "zfar") tmp = {m.zfar};
+    else if (k == "tex_rgb1") tmp = {m.tex_rgb1[0], m.tex_rgb1[1], m.tex_rgb1[2]};
+    else if (k == "tex_rgb2") tmp = {m.tex_rgb2[0], m.tex_rgb2[1], m.tex_rgb2[2]};
+    else if (k == "texrepeat") tmp = {m.texrepeat[0], m.texrepeat[1]};
+    else if (k == "sky_rgb1") tmp = {m.sky_rgb1[0], m.sky_rgb1[1], m.sky_rgb1[2]};
+    else if (k == "sky_rgb2") tmp = {m.sky_rgb2[0], m.sky_rgb2[1], m.sky_rgb2[2]};
     else if (k == "jnt_solref") tmp = {m.jnt_solref[0], m.jnt_solref[1]};
     else if (k == "jnt_solimp") tmp = {m.jnt_solimp[0], m.jnt_solimp[1], m.jnt_solimp[2], m.jnt_solimp[3], m.jnt_solimp[4]};
+    else if (k.rfind("mesh_tri:", 0) == 0) {
+      std::string mn = k.substr(9);
+      const HostMesh* hm = nullptr;
+      for (auto& x : m.meshes) if (x.name == mn) hm = &x;
+      if (!hm) return -1;
+      tmp.assign(hm->tri.begin(), hm->tri.end());
+    }
     else if (k.rfind("hull_verts:", 0) == 0 || k.rfind("mesh_pos:", 0) == 0 || k.rfind("mesh_quat:", 0) == 0 || k.rfind("mesh_volume:", 0) == 0 ||
              k.rfind("mesh_inertia:", 0) == 0) {
       std::string mn = k.substr(k.find(':') + 1);

@@ -1,0 +1,133 @@
+"""GPU: the observation builder (CUDA rasteriser + transform_depth + packing + intrinsic reward) against the oracle's
+fp64 ray caster (oracle/render.py) and the reference-pinned helper functions (oracle/envmath.py).
+
+Pixel parity with MuJoCo's OpenGL output is UNPINNED; these tests pin the product to its own stated
+rendering model.  Tolerances: depth within 1e-4 relative on >= 99 % of the pixels (silhouette pixels may flip between
+neighbouring surfaces in fp32), colour within +-2 grey levels on >= 98 %; scalar channels exact."""
+import numpy as np
+import pytest
+
+from helpers import oracle_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(scene, n=4, **kw):
+    from mujoco_rl_manipulate_unknown_objects_b200 import GripperSim, make_config
+    sim = GripperSim(make_config(sim_env="/xmls/%s_env.xml" % scene, **kw), num_envs=n, auto_reset=False)
+    return sim, oracle_model(sim)
+
+
+def _oracle_images(sim, om, qpos, cam, w, h):
+    from oracle import engine, render
+    sc = render.Scene(sim)
+    d = engine.Data(om)
+    d.qpos[:] = qpos
+    d.forward_position()
+    sub = np.array(np.ctypeslib.as_array(d.p.contents.subtree_com)[:om.nbody * 3]).reshape(-1, 3)
+    root = np.zeros(om.nbody, int)
+    par = om.md["body_parentid"]
+    for b in range(1, om.nbody):
+        r = b
+        while par[r] > 0:
+            r = par[r]
+        root[b] = r
+    cpos, cmat = render.camera_pose(sc, cam, d.xpos, d.xquat, sub[root])
+    return render.render(sc, d.geom_xpos, d.geom_xmat.reshape(-1, 3, 3), cpos, cmat, sc.cam_fovy[cam], w, h)
+
+
+@pytest.mark.parametrize("scene,cam", [("sand_ball", 2), ("sugar_cube", 2), ("sand_ball", 0), ("sand_ball", 1)])
+def test_raw_render_matches_ray_caster(scene, cam):
+    sim, om = _setup(scene)
+    st = sim.get_state()
+    q = st["qpos"].copy()
+    # four different poses: reset, gripper advanced and yawed, gripper rolled near the object, object tilted
+    q[1, 0] += 0.12; q[1, 4] = 0.4
+    q[2, 0] += 0.2; q[2, 2] += 0.1; q[2, 3] = 0.5; q[2, 5:7] = -0.3
+    q[3, 7:10] += [0.05, -0.1, 0.2]; q[3, 10:14] = np.array([0.9, 0.1, 0.3, -0.2]) / np.linalg.norm([0.9, 0.1, 0.3, -0.2])
+    sim.set_state(qpos=q)
+    W = H = 64
+    rgb, depth = sim.render(camera_id=cam, width=W, height=H)
+    rgb, depth = rgb.cpu().numpy(), depth.cpu().numpy()
+    for e in range(4):
+        orgb, odepth, ogeom = _oracle_images(sim, om, np.float64(q[e]), cam, W, H)
+        dok = np.abs(depth[e] - odepth) <= 1e-4 * np.maximum(1.0, np.abs(odepth))
+        cok = (np.abs(rgb[e].astype(int) - orgb.astype(int)).max(-1) <= 2)
+        print("[%s cam %d pose %d] depth ok %.4f colour ok %.4f  geoms seen %s" % (scene, cam, e, dok.mean(), cok.mean(), np.unique(ogeom).tolist()))
+        assert dok.mean() >= 0.99, "depth parity"
+        assert cok.mean() >= 0.98, "colour parity"
+        assert len(np.unique(ogeom)) >= 3  # sky / floor / at least one mesh in view
+    sim.close()
+
+
+def test_large_render_is_tiled_consistently():
+    """RobotEnv.render at 640x480 (robot_env.py:302-340) goes through 64x64 tiles: a 128x96 image must equal the oracle too."""
+    sim, om = _setup("sand_ball", n=1)
+    q = sim.get_state()["qpos"]
+    rgb, depth = sim.render(camera_id=0, width=128, height=96)
+    orgb, odepth, _ = _oracle_images(sim, om, np.float64(q[0]), 0, 128, 96)
+    dok = np.abs(depth[0].cpu().numpy() - odepth) <= 1e-4 * np.maximum(1.0, np.abs(odepth))
+    cok = np.abs(rgb[0].cpu().numpy().astype(int) - orgb.astype(int)).max(-1) <= 2
+    assert dok.mean() >= 0.99 and cok.mean() >= 0.98
+    sim.close()
+
+
+@pytest.mark.parametrize("full", [True, False])
+def test_observation_packing(full):
+    """obs = hwc_to_chw(dstack(rgb, transform_depth(depth), pad).astype(uint8)) (robot_env.py:275-293) from the device's own
+    raw images: RGB channels bit-exact, depth channel within one grey level (float32 reduction order), pad channel exact."""
+    import torch
+    from oracle import render
+    from mujoco_rl_manipulate_unknown_objects_b200._native import INFO as I
+    sim, _ = _setup("sugar_cube", n=8, full_observation=full)
+    sim.reset()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for _ in range(3):
+        a = torch.rand((8, 6), device="cuda", generator=gen) * 2 - 1
+        a[:, 0] = a[:, 0].abs()
+        sim.step(a)
+    obs = sim.obs.cpu().numpy()
+    info = sim.info.cpu().numpy()
+    rgb, depth = sim.render(camera_id=2, width=64, height=64)
+    rgb, depth = rgb.cpu().numpy(), depth.cpu().numpy()
+    C = 5 if full else 4
+    assert obs.shape == (8, C, 64, 64)
+    for e in range(8):
+        ref = render.observation(rgb[e], depth[e], info[e, I["GRASP"]], info[e, I["PHEROMONE"]], full)
+        np.testing.assert_array_equal(obs[e, :3], ref[:3])
+        np.testing.assert_array_equal(obs[e, C - 1], ref[C - 1])
+        assert obs[e, C - 1, 0, 0] == info[e, I["GRASP"]] and obs[e, C - 1, 0, 1] == info[e, I["PHEROMONE"]] and obs[e, C - 1].sum() == obs[e, C - 1, 0, :2].sum()
+        if full:
+            diff = np.abs(obs[e, 3].astype(int) - ref[3].astype(int))
+            assert diff.max() <= 1 and (diff > 0).mean() < 0.02
+            assert obs[e, 3].max() == 255 and obs[e, 3].min() == 0  # transform_depth saturates far pixels, zero at the nearest
+    sim.close()
+
+
+@pytest.mark.parametrize("full", [True, False])
+def test_intrinsic_reward(full):
+    """IntrinsicReward (reward.py:44-77): reward = progress reward + KL(old obs || new obs) of grey (and depth) histograms."""
+    import torch
+    from oracle import envmath, engine
+    from mujoco_rl_manipulate_unknown_objects_b200._native import INFO as I
+    N = 16
+    sim, _ = _setup("sand_ball", n=N, full_observation=full, im_reward=True)
+    sim.reset()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    L = engine.lib()
+    tdir, zero2 = np.array([1.0, 0.0]), np.zeros(2)
+    nonzero = 0
+    for t in range(4):
+        old = sim.obs.cpu().numpy().copy()
+        a = torch.rand((N, 6), device="cuda", generator=gen) * 2 - 1
+        sim.step(a)
+        new, rew, info = sim.obs.cpu().numpy(), sim.reward.cpu().numpy(), sim.info.cpu().numpy()
+        for e in range(N):
+            io = np.ascontiguousarray(info[e, I["INIT_OBJ_POS"]:I["INIT_OBJ_POS"] + 3], np.float64)
+            fo = np.ascontiguousarray(info[e, I["FINAL_OBJ_POS"]:I["FINAL_OBJ_POS"] + 3], np.float64)
+            pr = L.orc_agent_reward(io.ctypes.data, fo.ctypes.data, tdir.ctypes.data, int(info[e, I["GRIPPER_OPEN"]]), zero2.ctypes.data, int(info[e, I["OBJECT_GRASPED"]]))
+            ir = envmath.intrinsic_reward(old[e], new[e], full)
+            assert abs(rew[e] - (pr + ir)) <= 1e-4, (t, e, rew[e], pr, ir)
+            nonzero += ir > 1e-3
+    assert nonzero > N  # the images do change
+    sim.close()
