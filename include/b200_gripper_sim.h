@@ -137,6 +137,37 @@ GRS_API uint64_t grs_launch_count(const grs_sim* sim);
 /* average device time (ms) of the fused step kernel over the launches since the last call (CUDA events on the stream) */
 GRS_API float grs_step_kernel_ms(grs_sim* sim, int32_t reset_counters);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Policy inference during rollouts (tensor cores: tcgen05 + TMEM).  Replaces, for a whole batch of observations,
+ * `model.predict(obs, deterministic=...)` (reference eval_agent.py:57, SB3 SACPolicy._predict) = preprocess_obs (/255)
+ * -> AugmentedNatureCNN.forward (reference models/feature_extractor.py:39-49) -> actor latent_pi [256,256]
+ * (train_agent.py:18-20) -> mu / log_std -> tanh.
+ *
+ * Parameters travel as ONE flat fp32 array in torch state_dict order:
+ *   cnn.0.weight [32][C-1][8][8], cnn.0.bias [32], cnn.2.weight [64][32][4][4], cnn.2.bias [64],
+ *   cnn.4.weight [64][64][3][3], cnn.4.bias [64], linear.0.weight [512][n_flatten], linear.0.bias [512],
+ *   latent_pi.0.weight [256][514], latent_pi.0.bias [256], latent_pi.2.weight [256][256], latent_pi.2.bias [256],
+ *   mu.weight [A][256], mu.bias [A], log_std.weight [A][256], log_std.bias [A]
+ * (n_flatten = 64 * o3h * o3w; 1024 for 64x64 observations).  Arithmetic: bf16 operands, fp32 accumulation. */
+typedef struct grp_policy grp_policy;
+GRS_API const char* grp_last_error(void);
+GRS_API grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t height, int32_t width, int32_t action_dim, int32_t device);
+GRS_API void grp_destroy(grp_policy* p);
+GRS_API int64_t grp_num_params(const grp_policy* p);
+GRS_API int32_t grp_set_params(grp_policy* p, const float* params_host, int64_t count);
+GRS_API int32_t grp_get_params(const grp_policy* p, float* params_host, int64_t count);
+/* obs u8[n][C][H][W] (device) -> actions f32[n][A] (device).  noise_dev: f32[n][A] standard-normal samples for the
+ * stochastic action tanh(mu + exp(log_std) * noise), or NULL for the deterministic action tanh(mu).
+ * stream: cudaStream_t as void* (NULL = the handle's own stream). */
+GRS_API int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* actions_dev, const float* noise_dev, int32_t n, void* stream);
+/* named device buffers: "mu", "log_std" f32[max_envs][A]; "features" bf16[max_envs][576] (512 CNN + 2 direct + padding);
+ * "act1" "act2" "act3" "h1" "h2" bf16 intermediate activations (NHWC) */
+GRS_API int32_t grp_buffer(grp_policy* p, const char* name, void** ptr, uint64_t* bytes);
+/* {C, H, W, o1h, o1w, o2h, o2w, o3h, o3w, A} */
+GRS_API int32_t grp_shape(const grp_policy* p, int32_t* out10);
+GRS_API uint64_t grp_launch_count(const grp_policy* p);
+GRS_API void* grp_stream(const grp_policy* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,9 +34,8 @@ SYMBOLS = ["grs_last_error", "grs_default_config", "grs_create", "grs_destroy", 
            "grs_buffer", "grs_get_state", "grs_set_state", "grs_max_contacts", "grs_get_contacts", "grs_debug_step",
            "grs_model_get", "grs_model_get_int", "grs_model_names", "grs_compile_only", "grs_render", "grs_launch_count",
            "grs_step_kernel_ms"]
-POLICY_SYMBOLS = ["grp_create", "grp_destroy", "grp_num_params", "grp_set_params", "grp_get_params", "grp_forward", "grp_last_error"]
-if os.path.exists(os.path.join(HERE, "csrc", "policy_kernels.cu")):
-    SYMBOLS = SYMBOLS + POLICY_SYMBOLS
+SYMBOLS += ["grp_last_error", "grp_create", "grp_destroy", "grp_num_params", "grp_set_params", "grp_get_params", "grp_forward",
+            "grp_buffer", "grp_shape", "grp_launch_count", "grp_stream"]
 
 _lib = None
 
@@ -90,16 +89,21 @@ def load():
     L.grs_launch_count.argtypes = [vp]
     L.grs_step_kernel_ms.restype = C.c_float
     L.grs_step_kernel_ms.argtypes = [vp, i32]
-    if hasattr(L, "grp_create"):
-        L.grp_last_error.restype = C.c_char_p
-        L.grp_create.restype = vp
-        L.grp_create.argtypes = [i32, i32, i32, i32, i32, i32]
-        L.grp_destroy.argtypes = [vp]
-        L.grp_num_params.restype = i64
-        L.grp_num_params.argtypes = [vp]
-        L.grp_set_params.argtypes = [vp, vp, i64]
-        L.grp_get_params.argtypes = [vp, vp, i64]
-        L.grp_forward.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.grp_last_error.restype = C.c_char_p
+    L.grp_create.restype = vp
+    L.grp_create.argtypes = [i32, i32, i32, i32, i32, i32]
+    L.grp_destroy.argtypes = [vp]
+    L.grp_num_params.restype = i64
+    L.grp_num_params.argtypes = [vp]
+    L.grp_set_params.argtypes = [vp, vp, i64]
+    L.grp_get_params.argtypes = [vp, vp, i64]
+    L.grp_forward.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.grp_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(u64)]
+    L.grp_shape.argtypes = [vp, C.POINTER(i32)]
+    L.grp_launch_count.restype = u64
+    L.grp_launch_count.argtypes = [vp]
+    L.grp_stream.restype = vp
+    L.grp_stream.argtypes = [vp]
     _lib = L
     return L
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgripper_sim_b200.so")
 SOURCES = ["gripper_sim.cu", "policy_kernels.cu", "mjcf_compiler.cpp", "dev_model.cpp"]
-HEADERS = ["model.h", "sim_kernels.cuh", "env_kernels.cuh", "env_lockstep.cuh", "render_kernels.cuh", "policy_kernels.cuh",
+HEADERS = ["model.h", "sim_kernels.cuh", "env_kernels.cuh", "env_lockstep.cuh", "render_kernels.cuh",
            os.path.join("..", "..", "include", "b200_gripper_sim.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "-shared", "-diag-suppress", "550"]

@@ -1,0 +1,615 @@
+// Rollout-time policy inference on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Network (reference models/feature_extractor.py:19-49 `AugmentedNatureCNN` + the stable-baselines3 SAC actor built by
+// train_agent.py:18-20 with net_arch=[256,256]):
+//   obs u8 [N,C,H,W] --/255--> conv 8x8 s4 (C-1 -> 32) ReLU -> conv 4x4 s2 (32 -> 64) ReLU -> conv 3x3 s1 (64 -> 64) ReLU
+//   -> flatten -> linear (-> 512) ReLU -> concat obs[:, C-1, 0, 0:2]/255 (514) -> 256 ReLU -> 256 ReLU -> mu | log_std -> tanh
+//
+// Every layer is ONE kernel template, k_layer<MODE, BN, EPI>: an implicit GEMM  D[128 x BN] += A[128 x 64] * W[BN x 64]^T
+// per k-block, with
+//   * A gathered by the CTA's threads straight from the previous layer's activations (im2col on the fly, NHWC bf16; the
+//     first layer reads the uint8 observation planes and converts) into the canonical K-major SWIZZLE_128B shared-memory
+//     layout that tcgen05.mma reads through a shared-memory descriptor,
+//   * W (bf16, K-major, pre-permuted to the gather order on the host) staged the same way,
+//   * one elected thread issuing tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) into a TMEM accumulator and
+//     tcgen05.commit-ing each stage to an mbarrier, so the gather of k-block i+1.. overlaps the MMAs of k-block i
+//     (3-stage ring),
+//   * the epilogue reading the accumulator back with tcgen05.ld (32 lanes x 32 columns per warp), applying
+//     scale/bias/ReLU (or the squashed-Gaussian head) and writing bf16 NHWC rows for the next layer.
+// No cuBLAS / cuDNN / CUTLASS calls; descriptor bit layouts follow the PTX ISA (matrix-descriptor and instruction-descriptor
+// tables for tcgen05.mma).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_gripper_sim.h"
+
+namespace grp {
+
+enum Mode { DENSE = 0, CONV1 = 1, CONV2 = 2, CONV3 = 3 };
+enum Epi { EPI_RELU = 0, EPI_FEATURES = 1, EPI_HEAD = 2 };
+
+constexpr int BM = 128;      // rows of A per CTA = TMEM lanes = UMMA M
+constexpr int BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int THREADS = 128;
+constexpr int FEAT_LD = 576;  // 512 CNN features + 2 direct features, zero padded to a multiple of BK
+constexpr int HEAD_N = 16;    // mu rows 0..A-1, log_std rows 8..8+A-1
+
+struct LayerArgs {
+  const void* A;             // activations of the previous layer (u8 observation for CONV1, bf16 otherwise)
+  const __nv_bfloat16* W;    // [N_total][K] bf16, K-major
+  const float* bias;         // [N_total]
+  __nv_bfloat16* out;        // [M][ldo] bf16 (EPI_RELU / EPI_FEATURES)
+  int M, K, lda, ldo;
+  float scale;               // accumulator scale before the bias (1/255 folds the observation normalisation into conv1)
+  int C, H, W_;              // observation planes (CONV1, EPI_FEATURES)
+  int ih, iw, oh, ow;        // input / output feature-map size of a convolution
+  const unsigned char* obs;  // EPI_FEATURES: the two direct features come from obs[:, C-1, 0, 0:2]
+  // EPI_HEAD
+  float *mu, *log_std, *action;
+  const float* noise;        // [M][adim] standard normal, or NULL for the deterministic action
+  int adim;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns of the accumulator -> 16 registers per thread (thread t = lane 32*(warp%4)+t)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major operand, SWIZZLE_128B (rows of 128 bytes, 8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units            bits [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)   [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups             [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)                      [46,48)
+  d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B                            [61,64)
+  return d;
+}
+// instruction descriptor for kind::f16: D = fp32, A = B = bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// four uint8 -> four bf16 (exact)
+__device__ __forceinline__ void u8x4_to_bf16(uint32_t p, uint32_t& lo, uint32_t& hi) {
+  lo = pack_bf16((float)(p & 0xff), (float)((p >> 8) & 0xff));
+  hi = pack_bf16((float)((p >> 16) & 0xff), (float)(p >> 24));
+}
+
+// One 16-byte chunk (8 bf16) of A: row `r` (global row), k-block `kb`, chunk `ch` (0..7).  Rows >= M read as zero.
+template <int MODE>
+__device__ __forceinline__ uint4 load_a_chunk(const LayerArgs& a, int r, int kb, int ch) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (r >= a.M) return v;
+  if (MODE == DENSE) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.A) + (size_t)r * a.lda + kb * BK + ch * 8;
+    v = __ldg(reinterpret_cast<const uint4*>(p));
+  } else if (MODE == CONV1) {
+    // K order (c, ky, kx) = torch's [Cin][8][8]: k-block = input channel, chunk = kernel row, 8 pixels of one image row
+    const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.A) + (((size_t)n * a.C + kb) * a.ih + (4 * oy + ch)) * a.iw + 4 * ox;
+    const uint32_t p0 = __ldg(reinterpret_cast<const uint32_t*>(src)), p1 = __ldg(reinterpret_cast<const uint32_t*>(src + 4));
+    u8x4_to_bf16(p0, v.x, v.y);
+    u8x4_to_bf16(p1, v.z, v.w);
+  } else if (MODE == CONV2) {
+    // input NHWC with 32 channels, 4x4 stride 2; K order (ky, kx, c): k-block = (ky, kx pair) = 2 adjacent pixels = 128 bytes
+    const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
+    const int ky = kb >> 1, kx0 = (kb & 1) * 2;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.A) + (((size_t)n * a.ih + 2 * oy + ky) * a.iw + 2 * ox + kx0) * 32 + ch * 8;
+    v = __ldg(reinterpret_cast<const uint4*>(src));
+  } else {
+    // CONV3: input NHWC with 64 channels, 3x3 stride 1; k-block = one kernel tap = one pixel = 128 bytes
+    const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
+    const int ky = kb / 3, kx = kb - 3 * ky;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.A) + (((size_t)n * a.ih + oy + ky) * a.iw + ox + kx) * 64 + ch * 8;
+    v = __ldg(reinterpret_cast<const uint4*>(src));
+  }
+  return v;
+}
+
+template <int BN>
+__host__ __device__ constexpr int tmem_cols() { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256; }
+template <int BN>
+__host__ __device__ constexpr size_t layer_smem_bytes() { return (size_t)STAGES * (BM * 128 + BN * 128) + 1024; }
+
+template <int MODE, int BN, int EPI>
+__global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_stage[STAGES];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                         // STAGES x [128 rows x 128 B]
+  uint8_t* sB = smem + STAGES * BM * 128;     // STAGES x [BN rows x 128 B]
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&bar_stage[s], 1);
+    mbar_init(&bar_done, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols<BN>());
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int nkb = a.K / BK;
+  constexpr uint32_t idesc = instr_desc_bf16(BM, BN);
+
+#pragma unroll 1
+  for (int kb = 0; kb < nkb; kb++) {
+    const int s = kb % STAGES;
+    if (kb >= STAGES) {  // the MMAs that read this stage (k-block kb - STAGES) must have retired
+      mbar_wait(&bar_stage[s], ((kb / STAGES) - 1) & 1);
+      tc_fence_after();
+    }
+    uint8_t* dA = sA + s * BM * 128;
+    uint8_t* dB = sB + s * BN * 128;
+    // gather: 8 consecutive threads fetch the 8 chunks (128 contiguous bytes) of one row
+    uint4 va[BM * 8 / THREADS];
+#pragma unroll
+    for (int i = 0; i < BM * 8 / THREADS; i++) {
+      const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
+      va[i] = load_a_chunk<MODE>(a, m0 + row, kb, ch);
+    }
+#pragma unroll
+    for (int i = 0; i < BM * 8 / THREADS; i++) {
+      const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
+      *reinterpret_cast<uint4*>(dA + row * 128 + ((ch ^ (row & 7)) << 4)) = va[i];
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * 8 + THREADS - 1) / THREADS; i++) {
+      const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
+      if (c < BN * 8) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.W + (size_t)(n0 + row) * a.K + kb * BK + ch * 8));
+        *reinterpret_cast<uint4*>(dB + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+      }
+    }
+    fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aaddr = smem_u32(dA), baddr = smem_u32(dB);
+#pragma unroll
+      for (int k = 0; k < BK / 16; k++) {
+        const uint64_t ad = smem_desc_sw128(aaddr + k * 32), bd = smem_desc_sw128(baddr + k * 32);
+        umma_bf16(tmem, ad, bd, idesc, (kb | k) != 0);
+      }
+      umma_commit(&bar_stage[s]);
+      if (kb == nkb - 1) umma_commit(&bar_done);
+    }
+  }
+  mbar_wait(&bar_done, 0);
+  tc_fence_after();
+  __syncwarp();
+
+  // ---- epilogue: thread t of warp w owns accumulator row 32*w + t
+  const int row = m0 + warp * 32 + lane;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  if (EPI == EPI_HEAD) {
+    float v[16];
+    tmem_ld16(trow, v);
+    if (row < a.M) {
+      for (int k = 0; k < a.adim; k++) {
+        const float mu = v[k] + __ldg(a.bias + k);
+        float ls = v[8 + k] + __ldg(a.bias + 8 + k);
+        ls = fminf(fmaxf(ls, -20.0f), 2.0f);  // stable-baselines3 sac/policies.py LOG_STD_MIN / LOG_STD_MAX
+        float pre = mu;
+        if (a.noise) pre += __expf(ls) * a.noise[(size_t)row * a.adim + k];
+        a.mu[(size_t)row * a.adim + k] = mu;
+        a.log_std[(size_t)row * a.adim + k] = ls;
+        a.action[(size_t)row * a.adim + k] = tanhf(pre);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + c0, v);
+      if (row < a.M) {
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const float x = fmaxf(v[2 * k] * a.scale + __ldg(a.bias + n0 + c0 + 2 * k), 0.0f);
+          const float y = fmaxf(v[2 * k + 1] * a.scale + __ldg(a.bias + n0 + c0 + 2 * k + 1), 0.0f);
+          o[k] = pack_bf16(x, y);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)row * a.ldo + n0 + c0);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    if (EPI == EPI_FEATURES && blockIdx.y == 0 && row < a.M) {
+      // feature_extractor.py:42,48 — the two direct features ride behind the 512 CNN features (then zero padding)
+      const unsigned char* p = a.obs + ((size_t)row * a.C + (a.C - 1)) * a.H * a.W_;
+      uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)row * a.ldo + 512);
+      dst[0] = make_uint4(pack_bf16((float)p[0] * (1.0f / 255.0f), (float)p[1] * (1.0f / 255.0f)), 0, 0, 0);
+#pragma unroll
+      for (int k = 1; k < (FEAT_LD - 512) / 8; k++) dst[k] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols<BN>());
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static thread_local std::string g_err;
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+static uint16_t f2bf(float f) {  // round to nearest even
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+struct Shape {
+  int C, H, W, cin, o1h, o1w, o2h, o2w, o3h, o3w, nflat, adim;
+};
+
+}  // namespace grp
+
+using namespace grp;
+
+struct grp_policy {
+  Shape sh{};
+  int max_envs = 0, device = 0;
+  std::vector<float> params;  // fp32 master copy, torch state_dict order (see grp_num_params)
+  // device copies: bf16 K-major weights in gather order, fp32 biases
+  __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wfc = nullptr, *wp0 = nullptr, *wp1 = nullptr, *wh = nullptr;
+  float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *bfc = nullptr, *bp0 = nullptr, *bp1 = nullptr, *bh = nullptr;
+  // activations (bf16 NHWC) and outputs
+  __nv_bfloat16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *feat = nullptr, *h1 = nullptr, *h2 = nullptr;
+  float *mu = nullptr, *log_std = nullptr;
+  std::vector<void*> owned;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  bool have_params = false;
+};
+
+template <class T>
+static T* palloc(grp_policy* p, size_t count) {
+  void* d = nullptr;
+  CU(cudaMalloc(&d, count * sizeof(T)));
+  CU(cudaMemset(d, 0, count * sizeof(T)));
+  p->owned.push_back(d);
+  return (T*)d;
+}
+
+struct ParamLayout {
+  int64_t c1w, c1b, c2w, c2b, c3w, c3b, fcw, fcb, p0w, p0b, p1w, p1b, muw, mub, lsw, lsb, total;
+};
+static ParamLayout layout_of(const Shape& s) {
+  ParamLayout L{};
+  int64_t o = 0;
+  L.c1w = o; o += 32LL * s.cin * 64;
+  L.c1b = o; o += 32;
+  L.c2w = o; o += 64LL * 32 * 16;
+  L.c2b = o; o += 64;
+  L.c3w = o; o += 64LL * 64 * 9;
+  L.c3b = o; o += 64;
+  L.fcw = o; o += 512LL * s.nflat;
+  L.fcb = o; o += 512;
+  L.p0w = o; o += 256LL * 514;
+  L.p0b = o; o += 256;
+  L.p1w = o; o += 256LL * 256;
+  L.p1b = o; o += 256;
+  L.muw = o; o += (int64_t)s.adim * 256;
+  L.mub = o; o += s.adim;
+  L.lsw = o; o += (int64_t)s.adim * 256;
+  L.lsb = o; o += s.adim;
+  L.total = o;
+  return L;
+}
+
+extern "C" const char* grp_last_error(void) { return g_err.c_str(); }
+
+extern "C" grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t height, int32_t width, int32_t action_dim, int32_t device) {
+  try {
+    if (max_envs <= 0) throw std::runtime_error("max_envs must be positive");
+    if (channels < 2 || channels > 8) throw std::runtime_error("observation channels must be within 2..8 (image channels + the padding channel)");
+    if (action_dim < 1 || action_dim > 8) throw std::runtime_error("action_dim must be within 1..8");
+    if (width % 4 != 0) throw std::runtime_error("observation width must be a multiple of 4 (uint8 rows are read as 32-bit words)");
+    Shape s{};
+    s.C = channels; s.H = height; s.W = width; s.cin = channels - 1; s.adim = action_dim;
+    s.o1h = (height - 8) / 4 + 1; s.o1w = (width - 8) / 4 + 1;
+    s.o2h = (s.o1h - 4) / 2 + 1; s.o2w = (s.o1w - 4) / 2 + 1;
+    s.o3h = s.o2h - 2; s.o3w = s.o2w - 2;
+    if (height < 8 || width < 8 || s.o2h < 1 || s.o2w < 1 || s.o3h < 1 || s.o3w < 1) throw std::runtime_error("observation too small for the NatureCNN stack");
+    s.nflat = 64 * s.o3h * s.o3w;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device available: the policy has no CPU fallback");
+    if (device < 0 || device >= ndev) throw std::runtime_error("invalid CUDA device index");
+    int major = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) throw std::runtime_error("the policy kernels use tcgen05 / TMEM and need an sm_100-class GPU");
+    auto p = std::make_unique<grp_policy>();
+    p->sh = s; p->max_envs = max_envs; p->device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    const size_t N = max_envs;
+    p->params.assign(layout_of(s).total, 0.0f);
+    p->w1 = palloc<__nv_bfloat16>(p.get(), 32 * (size_t)s.cin * 64); p->b1 = palloc<float>(p.get(), 32);
+    p->w2 = palloc<__nv_bfloat16>(p.get(), 64 * 512); p->b2 = palloc<float>(p.get(), 64);
+    p->w3 = palloc<__nv_bfloat16>(p.get(), 64 * 576); p->b3 = palloc<float>(p.get(), 64);
+    p->wfc = palloc<__nv_bfloat16>(p.get(), 512 * (size_t)s.nflat); p->bfc = palloc<float>(p.get(), 512);
+    p->wp0 = palloc<__nv_bfloat16>(p.get(), 256 * (size_t)FEAT_LD); p->bp0 = palloc<float>(p.get(), 256);
+    p->wp1 = palloc<__nv_bfloat16>(p.get(), 256 * 256); p->bp1 = palloc<float>(p.get(), 256);
+    p->wh = palloc<__nv_bfloat16>(p.get(), HEAD_N * 256); p->bh = palloc<float>(p.get(), HEAD_N);
+    p->act1 = palloc<__nv_bfloat16>(p.get(), N * s.o1h * s.o1w * 32);
+    p->act2 = palloc<__nv_bfloat16>(p.get(), N * s.o2h * s.o2w * 64);
+    p->act3 = palloc<__nv_bfloat16>(p.get(), N * s.nflat);
+    p->feat = palloc<__nv_bfloat16>(p.get(), N * FEAT_LD);
+    p->h1 = palloc<__nv_bfloat16>(p.get(), N * 256);
+    p->h2 = palloc<__nv_bfloat16>(p.get(), N * 256);
+    p->mu = palloc<float>(p.get(), N * s.adim);
+    p->log_std = palloc<float>(p.get(), N * s.adim);
+#define SET_SMEM(M_, BN_, E_) CU(cudaFuncSetAttribute(k_layer<M_, BN_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer_smem_bytes<BN_>()))
+    SET_SMEM(CONV1, 32, EPI_RELU);
+    SET_SMEM(CONV2, 64, EPI_RELU);
+    SET_SMEM(CONV3, 64, EPI_RELU);
+    SET_SMEM(DENSE, 128, EPI_FEATURES);
+    SET_SMEM(DENSE, 128, EPI_RELU);
+    SET_SMEM(DENSE, HEAD_N, EPI_HEAD);
+#undef SET_SMEM
+    return p.release();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+extern "C" void grp_destroy(grp_policy* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  for (void* d : p->owned) cudaFree(d);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+extern "C" int64_t grp_num_params(const grp_policy* p) { return p ? layout_of(p->sh).total : 0; }
+
+static void upload_bf16(__nv_bfloat16* dst, const std::vector<uint16_t>& h) { CU(cudaMemcpy(dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice)); }
+static void upload_f32(float* dst, const float* h, size_t n) { CU(cudaMemcpy(dst, h, n * 4, cudaMemcpyHostToDevice)); }
+
+extern "C" int32_t grp_set_params(grp_policy* p, const float* host, int64_t count) {
+  if (!p || !host) { g_err = "null argument"; return 1; }
+  try {
+    const Shape& s = p->sh;
+    const ParamLayout L = layout_of(s);
+    if (count != L.total) throw std::runtime_error("parameter count mismatch: expected " + std::to_string(L.total) + ", got " + std::to_string(count));
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    std::memcpy(p->params.data(), host, (size_t)count * 4);
+    const float* P = p->params.data();
+    std::vector<uint16_t> h;
+    // conv1 [32][cin][8][8]: K order (c, ky, kx) is torch's own
+    h.resize(32 * (size_t)s.cin * 64);
+    for (size_t i = 0; i < h.size(); i++) h[i] = f2bf(P[L.c1w + i]);
+    upload_bf16(p->w1, h);
+    // conv2 [64][32][4][4] -> [64][(ky, kx, c)]
+    h.assign(64 * 512, 0);
+    for (int o = 0; o < 64; o++)
+      for (int c = 0; c < 32; c++)
+        for (int ky = 0; ky < 4; ky++)
+          for (int kx = 0; kx < 4; kx++) h[(size_t)o * 512 + (ky * 4 + kx) * 32 + c] = f2bf(P[L.c2w + (((size_t)o * 32 + c) * 4 + ky) * 4 + kx]);
+    upload_bf16(p->w2, h);
+    // conv3 [64][64][3][3] -> [64][(ky, kx, c)]
+    h.assign(64 * 576, 0);
+    for (int o = 0; o < 64; o++)
+      for (int c = 0; c < 64; c++)
+        for (int ky = 0; ky < 3; ky++)
+          for (int kx = 0; kx < 3; kx++) h[(size_t)o * 576 + (ky * 3 + kx) * 64 + c] = f2bf(P[L.c3w + (((size_t)o * 64 + c) * 3 + ky) * 3 + kx]);
+    upload_bf16(p->w3, h);
+    // linear [512][nflat], torch flatten order (c, y, x) -> activation order (y, x, c)
+    const int hw = s.o3h * s.o3w;
+    h.assign(512 * (size_t)s.nflat, 0);
+    for (int o = 0; o < 512; o++)
+      for (int c = 0; c < 64; c++)
+        for (int q = 0; q < hw; q++) h[(size_t)o * s.nflat + (size_t)q * 64 + c] = f2bf(P[L.fcw + (size_t)o * s.nflat + (size_t)c * hw + q]);
+    upload_bf16(p->wfc, h);
+    // latent_pi.0 [256][514] -> [256][576] zero padded
+    h.assign(256 * (size_t)FEAT_LD, 0);
+    for (int o = 0; o < 256; o++)
+      for (int k = 0; k < 514; k++) h[(size_t)o * FEAT_LD + k] = f2bf(P[L.p0w + (size_t)o * 514 + k]);
+    upload_bf16(p->wp0, h);
+    h.resize(256 * 256);
+    for (size_t i = 0; i < h.size(); i++) h[i] = f2bf(P[L.p1w + i]);
+    upload_bf16(p->wp1, h);
+    // head: rows 0.. = mu, rows 8.. = log_std
+    h.assign(HEAD_N * 256, 0);
+    std::vector<float> bh(HEAD_N, 0.0f);
+    for (int o = 0; o < s.adim; o++) {
+      for (int k = 0; k < 256; k++) {
+        h[(size_t)o * 256 + k] = f2bf(P[L.muw + (size_t)o * 256 + k]);
+        h[(size_t)(8 + o) * 256 + k] = f2bf(P[L.lsw + (size_t)o * 256 + k]);
+      }
+      bh[o] = P[L.mub + o];
+      bh[8 + o] = P[L.lsb + o];
+    }
+    upload_bf16(p->wh, h);
+    upload_f32(p->b1, P + L.c1b, 32);
+    upload_f32(p->b2, P + L.c2b, 64);
+    upload_f32(p->b3, P + L.c3b, 64);
+    upload_f32(p->bfc, P + L.fcb, 512);
+    upload_f32(p->bp0, P + L.p0b, 256);
+    upload_f32(p->bp1, P + L.p1b, 256);
+    upload_f32(p->bh, bh.data(), HEAD_N);
+    p->have_params = true;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+extern "C" int32_t grp_get_params(const grp_policy* p, float* host, int64_t count) {
+  if (!p || !host) { g_err = "null argument"; return 1; }
+  if (count != (int64_t)p->params.size()) { g_err = "parameter count mismatch"; return 1; }
+  std::memcpy(host, p->params.data(), (size_t)count * 4);
+  return 0;
+}
+
+template <int MODE, int BN, int EPI>
+static void launch_layer(grp_policy* p, const LayerArgs& a, int n_total, cudaStream_t st) {
+  dim3 grid((a.M + BM - 1) / BM, n_total / BN);
+  k_layer<MODE, BN, EPI><<<grid, THREADS, layer_smem_bytes<BN>(), st>>>(a);
+  CU(cudaGetLastError());
+  p->launches++;
+}
+
+extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* actions_dev, const float* noise_dev, int32_t n, void* stream) {
+  if (!p) { g_err = "null policy handle"; return 1; }
+  if (!obs_dev || !actions_dev) { g_err = "null device pointer"; return 1; }
+  if (n <= 0 || n > p->max_envs) { g_err = "n must be within 1..max_envs"; return 1; }
+  if (!p->have_params) { g_err = "grp_set_params has not been called"; return 1; }
+  try {
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+    const Shape& s = p->sh;
+    LayerArgs a{};
+    // conv1: uint8 planes -> [n*o1h*o1w][32]
+    a.A = obs_dev; a.W = p->w1; a.bias = p->b1; a.out = p->act1;
+    a.M = n * s.o1h * s.o1w; a.K = s.cin * 64; a.ldo = 32; a.scale = 1.0f / 255.0f;
+    a.C = s.C; a.H = s.H; a.W_ = s.W; a.ih = s.H; a.iw = s.W; a.oh = s.o1h; a.ow = s.o1w;
+    launch_layer<CONV1, 32, EPI_RELU>(p, a, 32, st);
+    // conv2
+    a = LayerArgs{};
+    a.A = p->act1; a.W = p->w2; a.bias = p->b2; a.out = p->act2;
+    a.M = n * s.o2h * s.o2w; a.K = 512; a.ldo = 64; a.scale = 1.0f;
+    a.ih = s.o1h; a.iw = s.o1w; a.oh = s.o2h; a.ow = s.o2w;
+    launch_layer<CONV2, 64, EPI_RELU>(p, a, 64, st);
+    // conv3
+    a = LayerArgs{};
+    a.A = p->act2; a.W = p->w3; a.bias = p->b3; a.out = p->act3;
+    a.M = n * s.o3h * s.o3w; a.K = 576; a.ldo = 64; a.scale = 1.0f;
+    a.ih = s.o2h; a.iw = s.o2w; a.oh = s.o3h; a.ow = s.o3w;
+    launch_layer<CONV3, 64, EPI_RELU>(p, a, 64, st);
+    // linear -> 512 features + the two direct features
+    a = LayerArgs{};
+    a.A = p->act3; a.W = p->wfc; a.bias = p->bfc; a.out = p->feat;
+    a.M = n; a.K = s.nflat; a.lda = s.nflat; a.ldo = FEAT_LD; a.scale = 1.0f;
+    a.C = s.C; a.H = s.H; a.W_ = s.W; a.obs = obs_dev;
+    launch_layer<DENSE, 128, EPI_FEATURES>(p, a, 512, st);
+    // latent_pi
+    a = LayerArgs{};
+    a.A = p->feat; a.W = p->wp0; a.bias = p->bp0; a.out = p->h1;
+    a.M = n; a.K = FEAT_LD; a.lda = FEAT_LD; a.ldo = 256; a.scale = 1.0f;
+    launch_layer<DENSE, 128, EPI_RELU>(p, a, 256, st);
+    a.A = p->h1; a.W = p->wp1; a.bias = p->bp1; a.out = p->h2; a.K = 256; a.lda = 256;
+    launch_layer<DENSE, 128, EPI_RELU>(p, a, 256, st);
+    // mu | log_std -> squashed Gaussian action
+    a = LayerArgs{};
+    a.A = p->h2; a.W = p->wh; a.bias = p->bh;
+    a.M = n; a.K = 256; a.lda = 256; a.scale = 1.0f;
+    a.mu = p->mu; a.log_std = p->log_std; a.action = actions_dev; a.noise = noise_dev; a.adim = s.adim;
+    launch_layer<DENSE, HEAD_N, EPI_HEAD>(p, a, HEAD_N, st);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+extern "C" int32_t grp_buffer(grp_policy* p, const char* name, void** ptr, uint64_t* bytes) {
+  if (!p || !name || !ptr) { g_err = "null argument"; return 1; }
+  const Shape& s = p->sh;
+  const size_t N = p->max_envs;
+  std::string k = name;
+  void* d = nullptr;
+  uint64_t sz = 0;
+  if (k == "mu") { d = p->mu; sz = N * s.adim * 4; }
+  else if (k == "log_std") { d = p->log_std; sz = N * s.adim * 4; }
+  else if (k == "features") { d = p->feat; sz = N * FEAT_LD * 2; }
+  else if (k == "act1") { d = p->act1; sz = N * s.o1h * s.o1w * 32 * 2; }
+  else if (k == "act2") { d = p->act2; sz = N * s.o2h * s.o2w * 64 * 2; }
+  else if (k == "act3") { d = p->act3; sz = N * (size_t)s.nflat * 2; }
+  else if (k == "h1") { d = p->h1; sz = N * 256 * 2; }
+  else if (k == "h2") { d = p->h2; sz = N * 256 * 2; }
+  else { g_err = "unknown buffer name '" + k + "'"; return 1; }
+  *ptr = d;
+  if (bytes) *bytes = sz;
+  return 0;
+}
+
+extern "C" int32_t grp_shape(const grp_policy* p, int32_t* out10) {
+  if (!p || !out10) { g_err = "null argument"; return 1; }
+  const Shape& s = p->sh;
+  const int v[10] = {s.C, s.H, s.W, s.o1h, s.o1w, s.o2h, s.o2w, s.o3h, s.o3w, s.adim};
+  for (int i = 0; i < 10; i++) out10[i] = v[i];
+  return 0;
+}
+
+extern "C" uint64_t grp_launch_count(const grp_policy* p) { return p ? p->launches : 0; }
+extern "C" void* grp_stream(const grp_policy* p) { return p ? (void*)p->stream : nullptr; }

@@ -1,0 +1,66 @@
+"""The C-ABI library loads and exports every entry point include/b200_gripper_sim.h declares; the CPU-only parts of the
+boundary (model compiler, configuration defaults, error reporting) behave; the product refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200_gripper_sim.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.findall(r"GRS_API\s+[\w\s\*]+?\b(gr[sp]_\w+)\s*\(", src)
+
+
+def test_library_exports_every_declared_symbol():
+    from mujoco_rl_manipulate_unknown_objects_b200 import _native
+    names = _declared()
+    assert len(names) >= 35 and "grs_step" in names and "grp_forward" in names
+    lib = C.CDLL(_native.lib_path())
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(set(names)) == sorted(set(_native.SYMBOLS)), "python binding and header list different entry points"
+
+
+def test_default_config_matches_reference_defaults():
+    """config/base_config.py:29-43 of the reference."""
+    from mujoco_rl_manipulate_unknown_objects_b200 import _native
+    lib = _native.load()
+    c = _native.GrsConfig()
+    lib.grs_default_config(C.byref(c))
+    assert (c.max_steps, c.time_horizon, c.include_roll, c.full_observation, c.im_reward, c.her_buffer, c.direction) == (400, 400, 1, 1, 0, 0, 0)
+    assert (c.width, c.height) == (64, 64)
+    assert np.allclose([c.pos_tolerance, c.grasp_tolerance, c.max_translation, c.max_rotation], [0.002, 0.03, 0.05, 0.15])
+
+
+def test_compile_only_handle_has_no_device_state():
+    from mujoco_rl_manipulate_unknown_objects_b200 import _native, compile_model
+    cm = compile_model("/xmls/sugar_cube_env.xml")
+    assert cm.sizes["nq"] == 14 and cm.sizes["nv"] == 13 and cm.sizes["nu"] == 7
+    lib = _native.load()
+    assert lib.grs_step(cm._h, None, None) != 0
+    assert b"compile_only" in lib.grs_last_error() or b"null" in lib.grs_last_error()
+    assert lib.grs_compile_only(b"/nonexistent/scene.xml") is None
+    assert len(lib.grs_last_error()) > 0
+    cm.close()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mujoco_rl_manipulate_unknown_objects_b200 import GripperSim, make_config
+    from mujoco_rl_manipulate_unknown_objects_b200.policy import GripperPolicy
+    with pytest.raises(RuntimeError):
+        GripperSim(make_config(sim_env="/xmls/sugar_cube_env.xml"), num_envs=2)
+    with pytest.raises(RuntimeError):
+        GripperPolicy(max_envs=2)
+    from mujoco_rl_manipulate_unknown_objects_b200 import _native
+    lib = _native.load()
+    assert lib.grs_create(b"x.xml", 2, None, 0) is None and b"CUDA" in lib.grs_last_error()
+    assert lib.grp_create(2, 5, 64, 64, 6, 0) is None and b"CUDA" in lib.grp_last_error()
