@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--direction", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--policy", action="store_true", help="actions from the tensor-core policy forward on the previous observation "
+                    "(device-resident rollout loop, BASELINE.json configs[3]) instead of U(-1,1)^6")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
     return ap.parse_args()
 
@@ -170,6 +172,17 @@ def run_ours(args):
     done_acc = torch.zeros(1, device=dev, dtype=torch.float64)
     ret_acc = torch.zeros(1, device=dev, dtype=torch.float64)
     c0, c1 = INFO["NSUB_A"], INFO["NSUB_A"] + 3
+    from mujoco_rl_manipulate_unknown_objects_b200.policy import GripperPolicy
+    policy = GripperPolicy(max_envs=N, obs_shape=sim.obs_shape, action_dim=sim.action_dim, device=local, seed=args.seed)
+    noise = torch.randn((W + K, N, sim.action_dim), device=dev, generator=gen)
+    pol_act = torch.empty((N, sim.action_dim), device=dev)
+
+    def one_step(i):
+        if args.policy:
+            policy.forward(sim.obs, deterministic=False, noise=noise[i], out=pol_act)
+            sim.step(pol_act)
+        else:
+            sim.step(actions[i])
 
     def barrier():
         if world > 1:
@@ -178,30 +191,42 @@ def run_ours(args):
 
     sim.reset()
     for i in range(W):
-        sim.step(actions[i])
+        one_step(i)
     barrier()
     sim.step_kernel_ms(reset=True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches0 = sim.launch_count
+    launches0 = sim.launch_count + policy.launch_count
     barrier()
     wall0 = time.perf_counter()
     for i in range(K):
         flush.zero_()  # L2 flush between timed iterations (outside the event pair)
         ev[i][0].record()
-        sim.step(actions[W + i])
+        one_step(W + i)
         ev[i][1].record()
         sub_acc += sim.info[:, c0:c1].sum()
         done_acc += sim.done.sum()
         ret_acc += sim.reward.sum()
     barrier()
     wall = time.perf_counter() - wall0
-    launches = sim.launch_count - launches0
+    launches = sim.launch_count + policy.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     kernel_ms = sim.step_kernel_ms(reset=True)
     clk = clocks.stop() if rank == 0 else None
+    # ---- policy forward alone on the last observation (tensor roofline): CUDA events on the launching stream, L2 flushed
+    pol_ms = []
+    for i in range(3 + 10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        policy.forward(sim.obs, out=pol_act)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if i >= 3:
+            pol_ms.append(e0.elapsed_time(e1))
+    pol_ms = float(np.median(pol_ms))
     # ---- end to end through the C-ABI with HOST buffers (the call a VecEnv makes): H2D actions, step, D2H results
     Cc, H, Wd = sim.obs_shape
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
@@ -223,7 +248,7 @@ def run_ours(args):
     d2h = h_obs.nbytes + h_rew.nbytes + h_done.nbytes + h_ag.nbytes + h_dg.nbytes + h_info.nbytes
     # ---- aggregate over ranks: units summed, time = max
     stats = torch.tensor([sub_acc.item(), float(N * K), done_acc.item(), ret_acc.item(), e2e_sub, float(launches)], device=dev, dtype=torch.float64)
-    tmax = torch.tensor([dev_ms, wall * 1e3, e2e_s * 1e3, kernel_ms], device=dev, dtype=torch.float64)
+    tmax = torch.tensor([dev_ms, wall * 1e3, e2e_s * 1e3, kernel_ms, pol_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # rollout-statistics reduction: the only collective on this path
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -234,8 +259,10 @@ def run_ours(args):
         value = substeps / dev_s
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": tmax[0] / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "%s_env (%s), %d envs/GPU, U(-1,1)^6 device-generated actions, physics + progress reward + RGB-D observation, auto-reset" % (
-                    args.scene, "synthetic stand-in mesh: acorn.stl is absent from the reference tree" if args.scene == "acorn" else "reference mesh", N),
+                "config": {"workload": "%s_env (%s), %d envs/GPU, %s, physics + progress reward + RGB-D observation, auto-reset" % (
+                    args.scene, "synthetic stand-in mesh: acorn.stl is absent from the reference tree" if args.scene == "acorn" else "reference mesh", N,
+                    "actions from the tcgen05 policy forward on the previous observation (random-init weights, stochastic)" if args.policy
+                    else "U(-1,1)^6 device-generated actions"),
                     "direction": args.direction, "envs_per_gpu": N, "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
                     "parallelism": "env-sharded x%d, no data-path collective" % world},
                 "transitions_per_s": transitions / dev_s, "substeps_per_transition": substeps / transitions, "episodes_finished": stats[2],
@@ -264,6 +291,13 @@ def run_ours(args):
                             "note": "fused kernel keeps state on chip: it is FP32-latency bound, not HBM bound (SURVEY.md §8d); "
                                     "per-transition accounting (%d B incl. the 20 480 B observation) gives %.1f GB/s over the whole step" % (
                                         BYTES_PER_TRANSITION, transitions / world / K * BYTES_PER_TRANSITION / (tmax[0] / K / 1e3) / 1e9)}
+        flop = 2 * (225 * 64 * (sim.obs_shape[0] - 1) * 32 + 36 * 512 * 64 + 16 * 576 * 64 + 1024 * 512 + 514 * 256 + 256 * 256 + 256 * 2 * sim.action_dim)
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1408.0))
+        tfl = N * flop / (tmax[4] / 1e3) / 1e12 if tmax[4] > 0 else None
+        line["policy"] = {"kernel": "k_layer x7 (tcgen05.mma kind::f16, TMEM accumulators): NatureCNN + actor MLP forward for %d observations" % N,
+                          "ms": tmax[4], "in_timed_region": bool(args.policy), "flop_per_obs": flop,
+                          "roofline": {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak if tfl else None,
+                                       "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cb = cpu_rollout(args.scene, args.direction, args.seed, args.cpu_seconds)
@@ -272,6 +306,7 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         print(json.dumps(line))
+    policy.close()
     sim.close()
     if world > 1:
         dist.destroy_process_group()
