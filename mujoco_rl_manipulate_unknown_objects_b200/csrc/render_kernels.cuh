@@ -115,6 +115,7 @@ struct TileShared {
   int nbig;
   float red[RTHREADS / 32 + 2];
   unsigned hist[2][256];
+  float dxs[TILE], dys[TILE];  // ray-direction components of the tile's pixel columns / rows (camera frame, z = -1)
 };
 
 __device__ __forceinline__ unsigned long long pack_frag(float depth, unsigned id) { return ((unsigned long long)__float_as_uint(depth) << 32) | id; }
@@ -157,9 +158,8 @@ __device__ __forceinline__ TriSetup tri_setup(const float* __restrict__ tri, con
   return s;
 }
 
-__device__ __forceinline__ void raster_pixel(const TriSetup& s, int px, int py, float ifx, float ify, int W, int H, int tx0, int ty0, float znear, float zfar, unsigned id,
-                                             unsigned long long* zbuf) {
-  float dx = ((2.0f * (px + 0.5f)) / W - 1.0f) * ifx, dy = (1.0f - (2.0f * (py + 0.5f)) / H) * ify;
+// One fragment.  dx, dy = ray direction of the pixel (from the tile tables), lx, ly = pixel coordinates inside the tile.
+__device__ __forceinline__ void raster_pixel(const TriSetup& s, float dx, float dy, int lx, int ly, float znear, float zfar, unsigned id, unsigned long long* zbuf) {
   float e0 = dx * s.c0[0] + dy * s.c0[1] - s.c0[2];
   float e1 = dx * s.c1[0] + dy * s.c1[1] - s.c1[2];
   float e2 = dx * s.c2[0] + dy * s.c2[1] - s.c2[2];
@@ -169,7 +169,26 @@ __device__ __forceinline__ void raster_pixel(const TriSetup& s, int px, int py, 
   if (sum == 0.0f) return;
   float t = s.det / sum;
   if (!(t >= znear && t <= zfar)) return;
-  atomicMin(&zbuf[(py - ty0) * TILE + (px - tx0)], pack_frag(t, id));
+  atomicMin(&zbuf[ly * TILE + lx], pack_frag(t, id));
+}
+
+// Conservative pixel span [lo, hi] of triangle `s` on the row with ray component dy: every edge function is affine in the
+// pixel column (e_k = alpha_k * px + beta_k), so each edge bounds the column range from one side.  The span is widened by a
+// pixel on both sides and the exact per-pixel test still decides, so the image is identical to testing the whole box.
+__device__ __forceinline__ void row_span(const TriSetup& s, float dy, float A, float B, int& lo, int& hi) {
+  const float sg = s.det > 0.0f ? 1.0f : -1.0f;
+  float flo = (float)s.x0, fhi = (float)s.x1;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float* c = k == 0 ? s.c0 : k == 1 ? s.c1 : s.c2;
+    const float alpha = sg * c[0] * A, beta = sg * (c[0] * B + dy * c[1] - c[2]);
+    if (alpha > 0.0f) flo = fmaxf(flo, -beta / alpha - 1.0f);
+    else if (alpha < 0.0f) fhi = fminf(fhi, -beta / alpha + 1.0f);
+    else if (beta < 0.0f) fhi = flo - 4.0f;  // the whole row is outside this edge
+  }
+  lo = max(s.x0, (int)floorf(flo));
+  hi = min(s.x1, (int)ceilf(fhi));
+  if (!(fhi >= flo - 2.0f)) hi = lo - 1;  // also catches NaN
 }
 
 struct Shade { float r, g, b; };
@@ -219,6 +238,8 @@ __device__ void render_tile(const RenderScene& sc, const float* __restrict__ rs,
   for (int i = tid; i < TILE * TILE; i += RTHREADS) sh.zbuf[i] = pack_frag(sc.zfar, 0xffffffffu);
   if (tid < 12) sh.cam[tid] = rs[84 + tid];
   if (tid == 0) sh.nbig = 0;
+  if (tid < TILE) sh.dxs[tid] = ((2.0f * ((tx0 + tid) + 0.5f)) / W - 1.0f) * ifx;
+  else if (tid < 2 * TILE) sh.dys[tid - TILE] = (1.0f - (2.0f * ((ty0 + tid - TILE) + 0.5f)) / H) * ify;
   __syncthreads();
   if (tid < sc.ngeom * 12) {
     int g = tid / 12, k = tid - g * 12;
@@ -248,7 +269,7 @@ __device__ void render_tile(const RenderScene& sc, const float* __restrict__ rs,
         if (q < BIGQ) { sh.bigq[q] = (g << 24) | t; continue; }
       }
       for (int py = s.y0; py <= s.y1; py++)
-        for (int px = s.x0; px <= s.x1; px++) raster_pixel(s, px, py, ifx, ify, W, H, tx0, ty0, sc.znear, sc.zfar, id, sh.zbuf);
+        for (int px = s.x0; px <= s.x1; px++) raster_pixel(s, sh.dxs[px - tx0], sh.dys[py - ty0], px - tx0, py - ty0, sc.znear, sc.zfar, id, sh.zbuf);
     }
   }
   __syncthreads();
@@ -259,11 +280,14 @@ __device__ void render_tile(const RenderScene& sc, const float* __restrict__ rs,
       int g = sh.bigq[q] >> 24, t = sh.bigq[q] & 0xffffff;
       TriSetup s = tri_setup(sc.tri + (size_t)(sc.geom_triadr[g] + t) * 9, sh.xf[g], fx, fy, W, H, tx0, ty0, tw, th, sc.znear);
       if (!s.ok) continue;
-      int bw = s.x1 - s.x0 + 1, area = bw * (s.y1 - s.y0 + 1);
       unsigned id = (unsigned)(sc.geom_triadr[g] + t);
-      for (int i = lane; i < area; i += 32) {
-        int py = s.y0 + i / bw, px = s.x0 + i % bw;
-        raster_pixel(s, px, py, ifx, ify, W, H, tx0, ty0, sc.znear, sc.zfar, id, sh.zbuf);
+      // dx(px) = A * px + B
+      const float A = 2.0f * ifx / (float)W, B = (1.0f / (float)W - 1.0f) * ifx;
+      for (int py = s.y0 + lane; py <= s.y1; py += 32) {  // one row per lane, only the columns the triangle can cover
+        const float dy = sh.dys[py - ty0];
+        int lo, hi;
+        row_span(s, dy, A, B, lo, hi);
+        for (int px = lo; px <= hi; px++) raster_pixel(s, sh.dxs[px - tx0], dy, px - tx0, py - ty0, sc.znear, sc.zfar, id, sh.zbuf);
       }
     }
   }
@@ -276,7 +300,7 @@ __device__ void render_tile(const RenderScene& sc, const float* __restrict__ rs,
     unsigned long long z = sh.zbuf[ly * TILE + lx];
     float depth = __uint_as_float((unsigned)(z >> 32));
     unsigned id = (unsigned)z;
-    float dx = ((2.0f * (px + 0.5f)) / W - 1.0f) * ifx, dy = (1.0f - (2.0f * (py + 0.5f)) / H) * ify;
+    float dx = sh.dxs[lx], dy = sh.dys[ly];
     // ray direction in the world (not normalised; camera-axis component = 1)
     float dw[3] = {cp[3] * dx + cp[4] * dy - cp[5], cp[6] * dx + cp[7] * dy - cp[8], cp[9] * dx + cp[10] * dy - cp[11]};
     int hit_geom = -1;
