@@ -608,15 +608,31 @@ __device__ __noinline__ void add_contact(const DevModel& m, WS& w, int pair, flo
 // engine_collision_driver.c : mj_collision over the candidate pair list (+ the bounding-sphere test of mj_collideGeoms)
 __device__ __noinline__ void collision(const DevModel& m, WS& w, const float4* hv, const int* __restrict__ adj, int lane) {
   if (lane == 0) { w.ncon = 0; w.overflow = 0; }
+  // broadphase for every candidate pair at once (lane = pair): plane / bounding-sphere rejection of mj_collideGeoms
+  bool cand = false;
+  if (lane < m.npair) {
+    const int g1 = m.pair_g1[lane], g2 = m.pair_g2[lane];
+    const float margin = m.pair_margin[lane];
+    float dif[3];
+    for (int k = 0; k < 3; k++) dif[k] = w.gpos[g2][k] - w.gpos[g1][k];
+    if (m.geom_type[g1] == GEOM_PLANE) {
+      const float* R1 = w.gmat[g1];
+      cand = !(dif[0] * R1[2] + dif[1] * R1[5] + dif[2] * R1[8] > margin + m.geom_rbound[g2]);
+    } else {
+      const float bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
+      cand = !(dot3(dif, dif) > bound * bound);
+    }
+  }
+  unsigned todo = __ballot_sync(FULL, cand);
   __syncwarp();
-  for (int p = 0; p < m.npair; p++) {
+  while (todo) {
+    const int p = __ffs(todo) - 1;
+    todo &= todo - 1;
     int g1 = m.pair_g1[p], g2 = m.pair_g2[p];
     float margin = m.pair_margin[p];
     if (m.geom_type[g1] == GEOM_PLANE) {
       const float* R1 = w.gmat[g1];
       float n[3] = {R1[2], R1[5], R1[8]}, dif[3];
-      for (int k = 0; k < 3; k++) dif[k] = w.gpos[g2][k] - w.gpos[g1][k];
-      if (dot3(dif, n) > margin + m.geom_rbound[g2]) continue;
       // mjc_PlaneConvex: support vertex, then its hull-graph neighbours that are also within the margin (<= 3 contacts)
       float nn[3] = {-n[0], -n[1], -n[2]}, v[3], pos[3];
       int vi = support_geom(m, w, hv, g2, nn, v, lane);
@@ -642,10 +658,6 @@ __device__ __noinline__ void collision(const DevModel& m, WS& w, const float4* h
         cnt++;
       }
     } else {
-      float dif[3];
-      for (int k = 0; k < 3; k++) dif[k] = w.gpos[g2][k] - w.gpos[g1][k];
-      float bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
-      if (dot3(dif, dif) > bound * bound) continue;
       float depth, dir[3], pos[3];
       // temporal coherence: a direction that separated the pair in the previous substep usually still does (one support
       // evaluation instead of a full MPR run).  It proves the origin lies outside the Minkowski difference, which is
@@ -866,7 +878,7 @@ __device__ __noinline__ float constraint_update(WS& w, int lane, bool want_cone_
   int state = 0;
   if (lane < nlim) {
     float x = w.e_jar[lane];
-    if (x < 0) { w.e_force[lane] = -w.e_D[lane] * x; cost = 0.5f * w.e_D[lane] * x * x; state = 1; w.e_act[lane] = 1; }
+    if (x < 0) { w.e_force[lane] = -w.e_D[lane] * x; cost = 0.5f * w.e_D[lane] * x * x; state = 1; w.e_act[lane] = w.e_D[lane]; }
     else { w.e_force[lane] = 0; w.e_act[lane] = 0; }
   } else if (lane < nitem) {
     int c = lane - nlim, r = nlim + 4 * c;
@@ -882,7 +894,7 @@ __device__ __noinline__ float constraint_update(WS& w, int lane, bool want_cone_
         float x = w.e_jar[r + j], D = w.e_D[r + j];
         w.e_force[r + j] = -D * x;
         cost += 0.5f * D * x * x;
-        w.e_act[r + j] = 1;
+        w.e_act[r + j] = D;
       }
       state = 1;
     } else {
@@ -974,16 +986,26 @@ __device__ __noinline__ float jt_force(const WS& w, int lane) {
   }
   return fc;
 }
-// Hessian H = M + J^T diag(act*D) J + cone blocks (lower triangle), engine_solver.c : MakeHessian / HessianCone
+// Lower-triangle entry lists of the 13x13 Hessian: all 91 entries (a contact couples gripper and object), or only the 49
+// entries of the two diagonal blocks (7 gripper dofs, 6 object dofs) when it does not.  Packed as (row << 4) | column.
+__constant__ unsigned char HESS_TRI[91] = {
+    0x00, 0x10, 0x11, 0x20, 0x21, 0x22, 0x30, 0x31, 0x32, 0x33, 0x40, 0x41, 0x42, 0x43, 0x44, 0x50, 0x51, 0x52, 0x53, 0x54, 0x55, 0x60, 0x61, 0x62, 0x63, 0x64,
+    0x65, 0x66, 0x77, 0x87, 0x88, 0x97, 0x98, 0x99, 0xa7, 0xa8, 0xa9, 0xaa, 0xb7, 0xb8, 0xb9, 0xba, 0xbb, 0xc7, 0xc8, 0xc9, 0xca, 0xcb, 0xcc,
+    // the 42 coupling entries (object rows x gripper columns)
+    0x70, 0x71, 0x72, 0x73, 0x74, 0x75, 0x76, 0x80, 0x81, 0x82, 0x83, 0x84, 0x85, 0x86, 0x90, 0x91, 0x92, 0x93, 0x94, 0x95, 0x96, 0xa0, 0xa1, 0xa2, 0xa3, 0xa4,
+    0xa5, 0xa6, 0xb0, 0xb1, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xc0, 0xc1, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6};
+
+// Hessian H = M + J^T diag(act*D) J + cone blocks (lower triangle only), engine_solver.c : MakeHessian / HessianCone.
+// w.e_act holds act*D per row.  One lane per lower-triangle entry: 2 passes when the trees are uncoupled, 3 otherwise.
 __device__ __noinline__ void make_hessian(WS& w, int lane) {
   const int nefc = w.nefc, nlim = w.nlim, ncon = w.ncon;
+  const int nent = w.coupled ? 91 : 49;
 #pragma unroll 1
-  for (int e = lane; e < NV * NV; e += 32) {
-    int a = e / NV, b = e - a * NV;
-    if (b > a) continue;
-    float h = w.M[e];
+  for (int i = lane; i < nent; i += 32) {
+    const int ab = HESS_TRI[i], a = ab >> 4, b = ab & 15;
+    float h = w.M[a * NV + b];
 #pragma unroll 4
-    for (int r = 0; r < nefc; r++) h += w.e_act[r] * w.e_D[r] * w.u.con.J[r][a] * w.u.con.J[r][b];
+    for (int r = 0; r < nefc; r++) h += w.e_act[r] * w.u.con.J[r][a] * w.u.con.J[r][b];
 #pragma unroll 1
     for (int c = 0; c < ncon; c++) {
       if (w.istate[nlim + c] != 2) continue;
@@ -993,7 +1015,7 @@ __device__ __noinline__ void make_hessian(WS& w, int lane) {
 #pragma unroll
       for (int j = 0; j < 4; j++) h += w.u.con.J[r + j][a] * (hc[4 * j] * jb0 + hc[4 * j + 1] * jb1 + hc[4 * j + 2] * jb2 + hc[4 * j + 3] * jb3);
     }
-    w.u.con.H[e] = h;
+    w.u.con.H[a * NV + b] = h;
   }
   __syncwarp();
 }
