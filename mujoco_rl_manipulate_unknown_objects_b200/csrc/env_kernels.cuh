@@ -363,11 +363,13 @@ struct SimBuffers {
   float* render_state;  // [N][RS_STRIDE]
   float* reset_record;  // [ST_STRIDE] state + [IN_STRIDE] info + [RS_STRIDE] render state of a freshly reset environment
   float* debug;         // [N][DEBUG_STRIDE]
-  int* queue;           // work-queue counter
+  int* queue;           // [0] work-queue counter, [1..2] bucket counters of the longest-first order
+  int* order;           // [N] environment ids, expected-long agent steps first (k_order_envs); identity for the other kernels
   const float4* hull;
   const int* adj;
   const DevModel* model;
   int n;
+  int ls_mask;  // lock-step kernel: which stage boundaries carry a block barrier (bit 0 smooth | 1 constraint | 2 solve | 3 euler+kin | 4 crb)
 };
 constexpr int DEBUG_STRIDE = 2048;
 constexpr int WARPS_PER_BLOCK = 4;

@@ -183,6 +183,20 @@ __device__ __noinline__ void env_writeback(const DevModel& m, const EnvCfg& c, c
   __syncwarp();
 }
 
+// Longest-first queue order.  An agent step is a chain of dependent substeps whose length is ragged and
+// largely known in advance: the gripper phase (robot_env.py:136-168, ~100-400 extra substeps) runs only when the open/close
+// action disagrees with the gripper's state.  The kernel's duration is the longest chain, so those environments must
+// start in the first wave; short ones fill the slots that free up.  Order within a bucket is irrelevant to the results.
+__global__ void k_order_envs(SimBuffers s, const float* __restrict__ actions, int adim) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= s.n) return;
+  const float oc = actions[(size_t)env * adim + adim - 1];
+  const bool open = s.state[(size_t)env * ST_STRIDE + ST_GRIPPER_OPEN] != 0.0f;
+  const bool is_long = (oc > 0.f && !open) || (oc < 0.f && open);
+  const int pos = is_long ? atomicAdd(s.queue + 1, 1) : s.n - 1 - atomicAdd(s.queue + 2, 1);
+  s.order[pos] = env;
+}
+
 #ifndef LS_BARRIERS
 #define LS_BARRIERS 4
 #endif
@@ -216,8 +230,9 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
       if (!dyn) env_writeback(m, c, s, w, t, lane);
     }
     if (t.stage == S_IDLE && !exhausted) {
-      int env = next_env(s.queue, lane);
-      if (env < s.n) {
+      int slot = next_env(s.queue, lane);
+      if (slot < s.n) {
+        const int env = __ldg(s.order + slot);
         t.env = env;
         load_state(w, t.f, s.state + (size_t)env * ST_STRIDE, lane);
         t.stage = S_LOADED;
@@ -234,25 +249,25 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
     LS_T0();
     if (dyn) smooth_forces(m, w, lane, true, t.f.xfrc_z);
     LS_T1(1);
-    if (LS_BARRIERS >= 6) __syncthreads();
+    if (s.ls_mask & 1) __syncthreads();
     LS_T0();
     if (dyn) make_constraint(m, w, lane);
     LS_T1(2);
-    __syncthreads();
+    if (s.ls_mask & 2) __syncthreads();
     iters = 0;
     LS_T0();
     if (dyn) iters = solve_newton(m, w, lane, m.iterations);
     LS_T1(3);
-    __syncthreads();
+    if (s.ls_mask & 4) __syncthreads();
     LS_T0();
     if (dyn) euler_integrate(m, w, lane);
     if (pos) kinematics(m, w, lane);
     LS_T1(4);
-    if (LS_BARRIERS >= 5) __syncthreads();
+    if (s.ls_mask & 8) __syncthreads();
     LS_T0();
     if (pos) com_pos_crb(m, w, lane);
     LS_T1(5);
-    __syncthreads();
+    if (s.ls_mask & 16) __syncthreads();
     LS_T0();
     if (pos) collision(m, w, s.hull, s.adj, lane);
     LS_T1(6);

@@ -60,7 +60,7 @@ struct grs_sim {
   int grid = 0;
   size_t smem = 0;
   // lock-step step kernel geometry (GRS_STEP_WARPS warps per block; 0 selects the sequential kernel)
-  int ls_warps = 10, ls_grid = 0;
+  int ls_warps = 8, ls_grid = 0;
   bool ls_timing = false;
   size_t ls_smem = 0;
 };
@@ -100,7 +100,7 @@ static void harvest_events(grs_sim* s) {
   s->ev_n = 0;
 }
 
-static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, sizeof(int), st)); }
+static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, 4 * sizeof(int), st)); }
 
 extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs_config* cfg_in, int32_t device) {
   grs_sim* raw = nullptr;
@@ -145,6 +145,9 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     b.reset_record = dalloc<float>(s.get(), ST_STRIDE + IN_STRIDE + RS_STRIDE);
     b.debug = dalloc<float>(s.get(), N * DEBUG_STRIDE);
     b.queue = dalloc<int>(s.get(), 4);
+    b.ls_mask = 22;
+    if (const char* e = getenv("GRS_LS_MASK")) b.ls_mask = atoi(e);
+    b.order = dalloc<int>(s.get(), N);
     const size_t obs_bytes = (size_t)s->C * s->H * s->W;
     s->d_obs = dalloc<unsigned char>(s.get(), N * obs_bytes);
     s->d_terminal_obs = dalloc<unsigned char>(s.get(), N * obs_bytes);
@@ -250,6 +253,7 @@ extern "C" int32_t grs_step(grs_sim* s, const float* actions_dev, void* stream) 
     launch_queue_kernel_prep(s, st);
     if (s->ev_n == grs_sim::NEV) harvest_events(s);
     CU(cudaEventRecord(s->ev0[s->ev_n], st));
+    if (s->ls_warps > 0) { k_order_envs<<<(s->n + 255) / 256, 256, 0, st>>>(s->b, actions_dev, s->adim); s->launches++; }
     if (s->ls_warps > 0 && s->ls_timing) k_env_step_ls<true><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
     else if (s->ls_warps > 0) k_env_step_ls<false><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
     else k_env_step<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
