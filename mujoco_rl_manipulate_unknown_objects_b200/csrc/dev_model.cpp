@@ -86,6 +86,7 @@ void build_dev_model(const HostModel& h, DevModel& d, std::vector<float>& hv4, s
     for (int k = 0; k < 3; k++) d.geom_pos[g][k] = (float)h.geom_pos[3 * g + k];
     for (int k = 0; k < 4; k++) d.geom_quat[g][k] = (float)h.geom_quat[4 * g + k];
     d.geom_rbound[g] = (float)h.geom_rbound[g];
+    for (int k = 0; k < 3; k++) d.geom_size[g][k] = (float)h.geom_size[3 * g + k];
     if (h.geom_meshid[g] >= 0) {
       const HostMesh& ms = h.meshes[h.geom_meshid[g]];
       int nvert = (int)ms.hull_verts.size() / 3;

@@ -88,7 +88,7 @@ struct DevModel {
   float dof_armature[NV + 3], dof_damping[NV + 3], dof_invweight0[NV + 3];
   // geoms
   int geom_type[MAXG], geom_body[MAXG], geom_hvadr[MAXG], geom_hvnum[MAXG], geom_adjadr[MAXG];
-  float geom_pos[MAXG][3], geom_quat[MAXG][4], geom_rbound[MAXG];
+  float geom_pos[MAXG][3], geom_quat[MAXG][4], geom_rbound[MAXG], geom_size[MAXG][3];
   // candidate pairs with mixed contact parameters (engine_collision_driver.c : mj_contactParam)
   int pair_g1[MAXPAIR], pair_g2[MAXPAIR];
   float pair_margin[MAXPAIR], pair_fric[MAXPAIR][3] /* slide, torsion, roll */, pair_solref[MAXPAIR][2], pair_solimp[MAXPAIR][5];

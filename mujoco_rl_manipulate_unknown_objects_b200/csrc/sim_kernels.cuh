@@ -633,6 +633,26 @@ __device__ __noinline__ void collision(const DevModel& m, WS& w, const float4* h
     if (m.geom_type[g1] == GEOM_PLANE) {
       const float* R1 = w.gmat[g1];
       float n[3] = {R1[2], R1[5], R1[8]}, dif[3];
+      if (m.geom_type[g2] == GEOM_BOX) {
+        // mjc_PlaneBox (engine_collision_primitive.c): corners in index order, lane = corner; the first 4 that lie within
+        // the margin and do not point away from the plane become contacts (gripper_two_fingers.xml:133)
+        for (int k = 0; k < 3; k++) dif[k] = w.gpos[g2][k] - w.gpos[g1][k];
+        const float dist = dot3(dif, n);
+        const int i = lane & 7;
+        float vec[3] = {(i & 1) ? m.geom_size[g2][0] : -m.geom_size[g2][0], (i & 2) ? m.geom_size[g2][1] : -m.geom_size[g2][1],
+                        (i & 4) ? m.geom_size[g2][2] : -m.geom_size[g2][2]}, corner[3];
+        mulmat3vec(corner, w.gmat[g2], vec);
+        const float ldist = dot3(n, corner);
+        unsigned ok = __ballot_sync(FULL, lane < 8 && !(dist + ldist > margin || ldist > 0));
+        for (int cnt = 0; ok && cnt < 4; cnt++) {
+          const int src = __ffs(ok) - 1;
+          ok &= ok - 1;
+          float cd = __shfl_sync(FULL, dist + ldist, src), pos[3];
+          for (int k = 0; k < 3; k++) pos[k] = __shfl_sync(FULL, corner[k], src) - 0.5f * cd * n[k] + w.gpos[g2][k];
+          add_contact(m, w, p, cd, pos, n, lane);
+        }
+        continue;
+      }
       // mjc_PlaneConvex: support vertex, then its hull-graph neighbours that are also within the margin (<= 3 contacts)
       float nn[3] = {-n[0], -n[1], -n[2]}, v[3], pos[3];
       int vi = support_geom(m, w, hv, g2, nn, v, lane);

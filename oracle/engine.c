@@ -122,7 +122,7 @@ int orc_set_d(OModel *m, const char *name, const double *v, int n) {
   FIELD_D(jnt_solimp, 5) FIELD_D(qpos0, O_MAXQ) FIELD_D(dof_armature, O_MAXV) FIELD_D(dof_damping, O_MAXV)
   FIELD_D(geom_pos, O_MAXG * 3) FIELD_D(geom_quat, O_MAXG * 4) FIELD_D(geom_friction, O_MAXG * 3)
   FIELD_D(geom_margin, O_MAXG) FIELD_D(geom_gap, O_MAXG) FIELD_D(geom_solref, O_MAXG * 2) FIELD_D(geom_solimp, O_MAXG * 5)
-  FIELD_D(geom_rbound, O_MAXG) FIELD_D(act_gear, O_MAXU) FIELD_D(act_ctrlrange, O_MAXU * 2)
+  FIELD_D(geom_rbound, O_MAXG) FIELD_D(geom_size, O_MAXG * 3) FIELD_D(act_gear, O_MAXU) FIELD_D(act_ctrlrange, O_MAXU * 2)
   FIELD_D(body_invweight0, O_MAXB * 2) FIELD_D(dof_invweight0, O_MAXV) SCALAR_D(meaninertia)
   return -1;
 }
@@ -585,6 +585,25 @@ static void collide_plane_mesh(const OModel *m, OData *d, int g1, int g2, double
     cnt++;
   }
 }
+/* engine_collision_primitive.c : mjc_PlaneBox — the corners in index order (bit 0 = x, 1 = y, 2 = z sign), keeping those
+ * within the margin that do not point away from the plane, at most 4 (gripper_two_fingers.xml:133 is the only box). */
+static void collide_plane_box(const OModel *m, OData *d, int g1, int g2, double margin) {
+  const double *R1 = d->geom_xmat + 9 * g1, *R2 = d->geom_xmat + 9 * g2, *sz = m->geom_size + 3 * g2;
+  double n[3] = {R1[2], R1[5], R1[8]}, dif[3], vec[3], corner[3], pos[3];
+  sub3(dif, d->geom_xpos + 3 * g2, d->geom_xpos + 3 * g1);
+  double dist = dot3(dif, n);
+  int cnt = 0;
+  for (int i = 0; i < 8 && cnt < 4; i++) {
+    vec[0] = (i & 1) ? sz[0] : -sz[0]; vec[1] = (i & 2) ? sz[1] : -sz[1]; vec[2] = (i & 4) ? sz[2] : -sz[2];
+    mulmat3vec(corner, R2, vec);
+    double ldist = dot3(n, corner);
+    if (dist + ldist > margin || ldist > 0) continue;
+    addscl3(pos, corner, n, -0.5 * (dist + ldist));
+    add3(pos, pos, d->geom_xpos + 3 * g2);
+    add_contact(m, d, g1, g2, dist + ldist, pos, n, margin);
+    cnt++;
+  }
+}
 /* engine_collision_convex.c : mjc_Convex (libccd MPR, one contact) */
 static void collide_convex(const OModel *m, OData *d, int g1, int g2, double margin) {
   double depth, dir[3], pos[3];
@@ -603,7 +622,8 @@ static void mj_collision(const OModel *m, OData *d) {
       double n[3] = {R1[2], R1[5], R1[8]}, dif[3];
       sub3(dif, d->geom_xpos + 3 * g2, d->geom_xpos + 3 * g1);
       if (dot3(dif, n) > margin + m->geom_rbound[g2]) continue;
-      collide_plane_mesh(m, d, g1, g2, margin);
+      if (m->geom_type[g2] == O_GEOM_BOX) collide_plane_box(m, d, g1, g2, margin);
+      else collide_plane_mesh(m, d, g1, g2, margin);
     } else {
       double dif[3];
       sub3(dif, d->geom_xpos + 3 * g2, d->geom_xpos + 3 * g1);

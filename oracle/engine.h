@@ -63,7 +63,7 @@ typedef struct {
   /* geoms */
   int geom_type[O_MAXG], geom_bodyid[O_MAXG], geom_meshid[O_MAXG], geom_condim[O_MAXG];
   double geom_pos[O_MAXG * 3], geom_quat[O_MAXG * 4], geom_friction[O_MAXG * 3], geom_margin[O_MAXG];
-  double geom_gap[O_MAXG], geom_solref[O_MAXG * 2], geom_solimp[O_MAXG * 5], geom_rbound[O_MAXG];
+  double geom_gap[O_MAXG], geom_solref[O_MAXG * 2], geom_solimp[O_MAXG * 5], geom_rbound[O_MAXG], geom_size[O_MAXG * 3];
   OMesh mesh[O_MAXM];
   /* actuators (motors) */
   int act_dofid[O_MAXU];

@@ -113,7 +113,7 @@ def lib():
 _D_FIELDS = ["gravity", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia",
              "jnt_pos", "jnt_axis", "jnt_range", "jnt_solref", "jnt_solimp", "qpos0", "dof_armature", "dof_damping",
              "geom_pos", "geom_quat", "geom_friction", "geom_margin", "geom_gap", "geom_solref", "geom_solimp",
-             "geom_rbound", "act_gear", "act_ctrlrange"]
+             "geom_rbound", "geom_size", "act_gear", "act_ctrlrange"]
 _I_FIELDS = ["body_parentid", "body_weldid", "body_jntadr", "body_jntnum", "body_dofadr", "body_dofnum",
              "jnt_type", "jnt_bodyid", "jnt_qposadr", "jnt_dofadr", "jnt_limited", "dof_bodyid", "dof_jntid",
              "dof_parentid", "geom_type", "geom_bodyid", "geom_meshid", "geom_condim", "act_dofid",

@@ -14,12 +14,13 @@ from mujoco_rl_manipulate_unknown_objects_b200._native import INFO as I
 pytestmark = pytest.mark.gpu
 
 CASES = [("sugar_cube", 0, {}, 3), ("sugar_cube", 45, {}, 4), ("sand_ball", 0, {}, 5), ("bread_crumb", 0, {}, 6), ("acorn", 0, {}, 7),
-         ("sand_ball", 45, dict(include_roll=False), 8), ("sugar_cube", 0, dict(her_buffer=True, time_horizon=12), 9)]
+         ("sand_ball", 45, dict(include_roll=False), 8), ("sugar_cube", 0, dict(her_buffer=True, time_horizon=12), 9),
+         ("gripper_two_fingers", 0, {}, 10)]  # the primitive-box scene (mjc_PlaneBox + box support in MPR)
 
 
 def make(scene, direction, kw, n, auto_reset=False):
     from mujoco_rl_manipulate_unknown_objects_b200 import GripperSim, make_config
-    cfg = make_config(sim_env="/xmls/%s_env.xml" % scene, direction=direction, **kw)
+    cfg = make_config(sim_env="/xmls/%s.xml" % (scene if scene == "gripper_two_fingers" else scene + "_env"), direction=direction, **kw)
     return GripperSim(cfg, num_envs=n, auto_reset=auto_reset)
 
 
