@@ -139,35 +139,39 @@ __device__ __forceinline__ void u8x4_to_bf16(uint32_t p, uint32_t& lo, uint32_t&
   hi = pack_bf16((float)((p >> 16) & 0xff), (float)(p >> 24));
 }
 
-// One 16-byte chunk (8 bf16) of A: row `r` (global row), k-block `kb`, chunk `ch` (0..7).  Rows >= M read as zero.
+// 16-byte asynchronous global -> shared copy (LDGSTS); `valid == false` zero-fills the destination (rows >= M)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Address of one 16-byte chunk (8 bf16) of A for the bf16 layers: row `r` (global row < M), k-block `kb`, chunk `ch` (0..7).
 template <int MODE>
-__device__ __forceinline__ uint4 load_a_chunk(const LayerArgs& a, int r, int kb, int ch) {
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (r >= a.M) return v;
+__device__ __forceinline__ const void* a_chunk_ptr(const LayerArgs& a, int r, int kb, int ch) {
   if (MODE == DENSE) {
-    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.A) + (size_t)r * a.lda + kb * BK + ch * 8;
-    v = __ldg(reinterpret_cast<const uint4*>(p));
-  } else if (MODE == CONV1) {
-    // K order (c, ky, kx) = torch's [Cin][8][8]: k-block = input channel, chunk = kernel row, 8 pixels of one image row
-    const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.A) + (((size_t)n * a.C + kb) * a.ih + (4 * oy + ch)) * a.iw + 4 * ox;
-    const uint32_t p0 = __ldg(reinterpret_cast<const uint32_t*>(src)), p1 = __ldg(reinterpret_cast<const uint32_t*>(src + 4));
-    u8x4_to_bf16(p0, v.x, v.y);
-    u8x4_to_bf16(p1, v.z, v.w);
+    return reinterpret_cast<const __nv_bfloat16*>(a.A) + (size_t)r * a.lda + kb * BK + ch * 8;
   } else if (MODE == CONV2) {
     // input NHWC with 32 channels, 4x4 stride 2; K order (ky, kx, c): k-block = (ky, kx pair) = 2 adjacent pixels = 128 bytes
     const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
     const int ky = kb >> 1, kx0 = (kb & 1) * 2;
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.A) + (((size_t)n * a.ih + 2 * oy + ky) * a.iw + 2 * ox + kx0) * 32 + ch * 8;
-    v = __ldg(reinterpret_cast<const uint4*>(src));
+    return reinterpret_cast<const __nv_bfloat16*>(a.A) + (((size_t)n * a.ih + 2 * oy + ky) * a.iw + 2 * ox + kx0) * 32 + ch * 8;
   } else {
     // CONV3: input NHWC with 64 channels, 3x3 stride 1; k-block = one kernel tap = one pixel = 128 bytes
     const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
     const int ky = kb / 3, kx = kb - 3 * ky;
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.A) + (((size_t)n * a.ih + oy + ky) * a.iw + ox + kx) * 64 + ch * 8;
-    v = __ldg(reinterpret_cast<const uint4*>(src));
+    return reinterpret_cast<const __nv_bfloat16*>(a.A) + (((size_t)n * a.ih + oy + ky) * a.iw + ox + kx) * 64 + ch * 8;
   }
-  return v;
+}
+// CONV1: the 8 raw uint8 pixels of one chunk.  K order (c, ky, kx) = torch's [Cin][8][8]: k-block = input channel,
+// chunk = kernel row, 8 pixels of one image row.  Rows >= M read as zero.
+__device__ __forceinline__ uint2 conv1_raw_chunk(const LayerArgs& a, int r, int kb, int ch) {
+  if (r >= a.M) return make_uint2(0, 0);
+  const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(a.A) + (((size_t)n * a.C + kb) * a.ih + (4 * oy + ch)) * a.iw + 4 * ox;
+  return make_uint2(__ldg(reinterpret_cast<const uint32_t*>(src)), __ldg(reinterpret_cast<const uint32_t*>(src + 4)));
 }
 
 template <int BN>
@@ -200,47 +204,104 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
   const int nkb = a.K / BK;
   constexpr uint32_t idesc = instr_desc_bf16(BM, BN);
 
-#pragma unroll 1
-  for (int kb = 0; kb < nkb; kb++) {
+  // elected thread: the four K=16 MMAs of one staged k-block, committed to the stage's barrier
+  auto issue_mma = [&](int kb) {
     const int s = kb % STAGES;
-    if (kb >= STAGES) {  // the MMAs that read this stage (k-block kb - STAGES) must have retired
-      mbar_wait(&bar_stage[s], ((kb / STAGES) - 1) & 1);
-      tc_fence_after();
-    }
-    uint8_t* dA = sA + s * BM * 128;
-    uint8_t* dB = sB + s * BN * 128;
-    // gather: 8 consecutive threads fetch the 8 chunks (128 contiguous bytes) of one row
-    uint4 va[BM * 8 / THREADS];
+    tc_fence_after();
+    const uint32_t aaddr = smem_u32(sA + s * BM * 128), baddr = smem_u32(sB + s * BN * 128);
 #pragma unroll
-    for (int i = 0; i < BM * 8 / THREADS; i++) {
-      const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
-      va[i] = load_a_chunk<MODE>(a, m0 + row, kb, ch);
+    for (int k = 0; k < BK / 16; k++) {
+      const uint64_t ad = smem_desc_sw128(aaddr + k * 32), bd = smem_desc_sw128(baddr + k * 32);
+      umma_bf16(tmem, ad, bd, idesc, (kb | k) != 0);
     }
-#pragma unroll
-    for (int i = 0; i < BM * 8 / THREADS; i++) {
-      const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
-      *reinterpret_cast<uint4*>(dA + row * 128 + ((ch ^ (row & 7)) << 4)) = va[i];
-    }
+    umma_commit(&bar_stage[s]);
+    if (kb == nkb - 1) umma_commit(&bar_done);
+  };
+  // W tile of k-block kb -> stage (asynchronous copies, swizzled destination)
+  auto copy_w = [&](int kb) {
+    const uint32_t dB = smem_u32(sB + (kb % STAGES) * BN * 128);
 #pragma unroll
     for (int i = 0; i < (BN * 8 + THREADS - 1) / THREADS; i++) {
       const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
-      if (c < BN * 8) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.W + (size_t)(n0 + row) * a.K + kb * BK + ch * 8));
-        *reinterpret_cast<uint4*>(dB + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+      if (c < BN * 8) cp_async16(dB + row * 128 + ((ch ^ (row & 7)) << 4), a.W + (size_t)(n0 + row) * a.K + kb * BK + ch * 8, true);
+    }
+  };
+
+  if (MODE == CONV1) {
+    // The observation is uint8 and has to pass through registers (u8 -> bf16 is exact).  All the raw loads of up to four
+    // k-blocks (= input channels) are issued before the first use, so a CTA pays the global-memory latency once, not
+    // once per k-block.
+    constexpr int PRE = 4;
+#pragma unroll 1
+    for (int kb0 = 0; kb0 < nkb; kb0 += PRE) {
+      uint2 raw[PRE][BM * 8 / THREADS];
+#pragma unroll
+      for (int j = 0; j < PRE; j++)
+#pragma unroll
+        for (int i = 0; i < BM * 8 / THREADS; i++) {
+          const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
+          raw[j][i] = kb0 + j < nkb ? conv1_raw_chunk(a, m0 + row, kb0 + j, ch) : make_uint2(0, 0);
+        }
+#pragma unroll
+      for (int j = 0; j < PRE; j++) {
+        const int kb = kb0 + j;
+        if (kb < nkb) {
+          const int s = kb % STAGES;
+          if (kb >= STAGES) {  // the MMAs that read this stage (k-block kb - STAGES) must have retired
+            mbar_wait(&bar_stage[s], ((kb / STAGES) - 1) & 1);
+            tc_fence_after();
+          }
+          copy_w(kb);
+          cp_async_commit();
+          uint8_t* dA = sA + s * BM * 128;
+#pragma unroll
+          for (int i = 0; i < BM * 8 / THREADS; i++) {
+            const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
+            uint4 v;
+            u8x4_to_bf16(raw[j][i].x, v.x, v.y);
+            u8x4_to_bf16(raw[j][i].y, v.z, v.w);
+            *reinterpret_cast<uint4*>(dA + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+          }
+          cp_async_wait<0>();
+          fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+          __syncthreads();
+          if (tid == 0) issue_mma(kb);
+        }
       }
     }
-    fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t aaddr = smem_u32(dA), baddr = smem_u32(dB);
+  } else {
+    // bf16 activations: A and W tiles are straight 16-byte copies, so they go global -> shared asynchronously (LDGSTS),
+    // STAGES - 1 k-blocks ahead of the MMAs; no registers, no per-k-block latency exposure.
+    auto copy_stage = [&](int kb) {
+      const uint32_t dA = smem_u32(sA + (kb % STAGES) * BM * 128);
 #pragma unroll
-      for (int k = 0; k < BK / 16; k++) {
-        const uint64_t ad = smem_desc_sw128(aaddr + k * 32), bd = smem_desc_sw128(baddr + k * 32);
-        umma_bf16(tmem, ad, bd, idesc, (kb | k) != 0);
+      for (int i = 0; i < BM * 8 / THREADS; i++) {
+        const int c = i * THREADS + tid, row = c >> 3, ch = c & 7, r = m0 + row;
+        const bool valid = r < a.M;
+        cp_async16(dA + row * 128 + ((ch ^ (row & 7)) << 4), valid ? a_chunk_ptr<MODE>(a, r, kb, ch) : a.A, valid);
       }
-      umma_commit(&bar_stage[s]);
-      if (kb == nkb - 1) umma_commit(&bar_done);
+      copy_w(kb);
+    };
+#pragma unroll
+    for (int kb = 0; kb < STAGES - 1; kb++) {
+      if (kb < nkb) copy_stage(kb);
+      cp_async_commit();
+    }
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; kb++) {
+      const int kn = kb + STAGES - 1;  // refill the stage that k-block kb - 1 used, once its MMAs have retired
+      if (kn < nkb) {
+        if (kb >= 1) {
+          mbar_wait(&bar_stage[(kb - 1) % STAGES], ((kb - 1) / STAGES) & 1);
+          tc_fence_after();
+        }
+        copy_stage(kn);
+      }
+      cp_async_commit();
+      cp_async_wait<STAGES - 1>();  // k-block kb has landed (this thread's copies; the barrier below covers the others)
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) issue_mma(kb);
     }
   }
   mbar_wait(&bar_done, 0);
