@@ -124,19 +124,14 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B                            [61,64)
   return d;
 }
-// instruction descriptor for kind::f16: D = fp32, A = B = bf16, both K-major, M x N
-__host__ __device__ constexpr uint32_t instr_desc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// instruction descriptor for kind::f16: D = fp32, A = B = bf16 (format 1) or fp16 (format 0), both K-major, M x N
+__host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n, bool bf16) {
+  return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
-}
-// four uint8 -> four bf16 (exact)
-__device__ __forceinline__ void u8x4_to_bf16(uint32_t p, uint32_t& lo, uint32_t& hi) {
-  lo = pack_bf16((float)(p & 0xff), (float)((p >> 8) & 0xff));
-  hi = pack_bf16((float)((p >> 16) & 0xff), (float)(p >> 24));
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); `valid == false` zero-fills the destination (rows >= M)
@@ -148,30 +143,39 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Address of one 16-byte chunk (8 bf16) of A for the bf16 layers: row `r` (global row < M), k-block `kb`, chunk `ch` (0..7).
+// Implicit-GEMM addressing, split into a per-row part (computed once per CTA: the integer divisions) and a per-k-block part.
+// Element offset (in units of the input type) of row `r`, chunk `ch` at k-block 0; rows >= M return -1.
+//   DENSE  row-major [M][lda]: chunk = 8 consecutive bf16
+//   CONV1  uint8 planes [n][C][ih][iw], 8x8 stride 4, K order (c, ky, kx) = torch's [Cin][8][8]: k-block = input channel,
+//          chunk = kernel row ky, the 8 pixels of one image row
+//   CONV2  NHWC bf16, 32 channels, 4x4 stride 2, K order (ky, kx, c): k-block = (ky, kx pair) = 2 adjacent pixels = 128 bytes
+//   CONV3  NHWC bf16, 64 channels, 3x3 stride 1: k-block = one kernel tap = one pixel = 128 bytes
 template <int MODE>
-__device__ __forceinline__ const void* a_chunk_ptr(const LayerArgs& a, int r, int kb, int ch) {
-  if (MODE == DENSE) {
-    return reinterpret_cast<const __nv_bfloat16*>(a.A) + (size_t)r * a.lda + kb * BK + ch * 8;
-  } else if (MODE == CONV2) {
-    // input NHWC with 32 channels, 4x4 stride 2; K order (ky, kx, c): k-block = (ky, kx pair) = 2 adjacent pixels = 128 bytes
-    const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
-    const int ky = kb >> 1, kx0 = (kb & 1) * 2;
-    return reinterpret_cast<const __nv_bfloat16*>(a.A) + (((size_t)n * a.ih + 2 * oy + ky) * a.iw + 2 * ox + kx0) * 32 + ch * 8;
-  } else {
-    // CONV3: input NHWC with 64 channels, 3x3 stride 1; k-block = one kernel tap = one pixel = 128 bytes
-    const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
-    const int ky = kb / 3, kx = kb - 3 * ky;
-    return reinterpret_cast<const __nv_bfloat16*>(a.A) + (((size_t)n * a.ih + oy + ky) * a.iw + ox + kx) * 64 + ch * 8;
-  }
-}
-// CONV1: the 8 raw uint8 pixels of one chunk.  K order (c, ky, kx) = torch's [Cin][8][8]: k-block = input channel,
-// chunk = kernel row, 8 pixels of one image row.  Rows >= M read as zero.
-__device__ __forceinline__ uint2 conv1_raw_chunk(const LayerArgs& a, int r, int kb, int ch) {
-  if (r >= a.M) return make_uint2(0, 0);
+__device__ __forceinline__ int a_row_base(const LayerArgs& a, int r, int ch) {
+  if (r >= a.M) return -1;
+  if (MODE == DENSE) return r * a.lda + ch * 8;
   const int per = a.oh * a.ow, n = r / per, p = r - n * per, oy = p / a.ow, ox = p - oy * a.ow;
-  const unsigned char* src = reinterpret_cast<const unsigned char*>(a.A) + (((size_t)n * a.C + kb) * a.ih + (4 * oy + ch)) * a.iw + 4 * ox;
-  return make_uint2(__ldg(reinterpret_cast<const uint32_t*>(src)), __ldg(reinterpret_cast<const uint32_t*>(src + 4)));
+  if (MODE == CONV1) return ((n * a.C) * a.ih + (4 * oy + ch)) * a.iw + 4 * ox;
+  if (MODE == CONV2) return ((n * a.ih + 2 * oy) * a.iw + 2 * ox) * 32 + ch * 8;
+  return ((n * a.ih + oy) * a.iw + ox) * 64 + ch * 8;
+}
+template <int MODE>
+__device__ __forceinline__ int a_kb_offset(const LayerArgs& a, int kb) {
+  if (MODE == DENSE) return kb * BK;
+  if (MODE == CONV1) return kb * a.ih * a.iw;
+  if (MODE == CONV2) return ((kb >> 1) * a.iw + (kb & 1) * 2) * 32;
+  return ((kb / 3) * a.iw + (kb % 3)) * 64;
+}
+// eight uint8 -> eight fp16, exact: the byte lands in the mantissa of 1024.0 (0x6400 | b = 1024 + b), then 1024 is subtracted
+__device__ __forceinline__ uint32_t u8x2_to_f16x2(uint32_t p, uint32_t sel) {
+  uint32_t v;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(p), "r"(0x64646464u), "r"(sel));
+  __half2 h = __hsub2(*reinterpret_cast<__half2*>(&v), __half2half2(__ushort_as_half((unsigned short)0x6400)));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 u8x8_to_f16x8(uint2 raw) {
+  // prmt selectors: result bytes {b0, 0x64, b1, 0x64} -> halves (0x6400 | b0), (0x6400 | b1); source bytes 4..7 are the constant
+  return make_uint4(u8x2_to_f16x2(raw.x, 0x4140u), u8x2_to_f16x2(raw.x, 0x4342u), u8x2_to_f16x2(raw.y, 0x4140u), u8x2_to_f16x2(raw.y, 0x4342u));
 }
 
 template <int BN>
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
   const uint32_t tmem = tmem_base_s;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int nkb = a.K / BK;
-  constexpr uint32_t idesc = instr_desc_bf16(BM, BN);
+  constexpr uint32_t idesc = instr_desc_f16(BM, BN, MODE != CONV1);
 
   // elected thread: the four K=16 MMAs of one staged k-block, committed to the stage's barrier
   auto issue_mma = [&](int kb) {
@@ -227,21 +231,37 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
     }
   };
 
+  // this thread's 8 (row, chunk) pairs: input offset at k-block 0 and swizzled offset inside a stage (constant over k-blocks)
+  int rbase[BM * 8 / THREADS], soff[BM * 8 / THREADS];
+#pragma unroll
+  for (int i = 0; i < BM * 8 / THREADS; i++) {
+    const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
+    rbase[i] = a_row_base<MODE>(a, m0 + row, ch);
+    soff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
+  }
+
   if (MODE == CONV1) {
-    // The observation is uint8 and has to pass through registers (u8 -> bf16 is exact).  All the raw loads of up to four
+    // The observation is uint8 and has to pass through registers (u8 -> fp16 is exact; this layer's weights are fp16 too).  All the raw loads of up to four
     // k-blocks (= input channels) are issued before the first use, so a CTA pays the global-memory latency once, not
     // once per k-block.
     constexpr int PRE = 4;
+    const unsigned char* obs = reinterpret_cast<const unsigned char*>(a.A);
+    const int plane = a_kb_offset<CONV1>(a, 1);
 #pragma unroll 1
     for (int kb0 = 0; kb0 < nkb; kb0 += PRE) {
       uint2 raw[PRE][BM * 8 / THREADS];
 #pragma unroll
-      for (int j = 0; j < PRE; j++)
+      for (int i = 0; i < BM * 8 / THREADS; i++) {
+        const int base = rbase[i];
 #pragma unroll
-        for (int i = 0; i < BM * 8 / THREADS; i++) {
-          const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
-          raw[j][i] = kb0 + j < nkb ? conv1_raw_chunk(a, m0 + row, kb0 + j, ch) : make_uint2(0, 0);
+        for (int j = 0; j < PRE; j++) {
+          raw[j][i] = make_uint2(0, 0);
+          if (base >= 0 && kb0 + j < nkb) {
+            const unsigned char* src = obs + base + (kb0 + j) * plane;
+            raw[j][i] = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(src)), __ldg(reinterpret_cast<const uint32_t*>(src + 4)));
+          }
         }
+      }
 #pragma unroll
       for (int j = 0; j < PRE; j++) {
         const int kb = kb0 + j;
@@ -255,13 +275,7 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
           cp_async_commit();
           uint8_t* dA = sA + s * BM * 128;
 #pragma unroll
-          for (int i = 0; i < BM * 8 / THREADS; i++) {
-            const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
-            uint4 v;
-            u8x4_to_bf16(raw[j][i].x, v.x, v.y);
-            u8x4_to_bf16(raw[j][i].y, v.z, v.w);
-            *reinterpret_cast<uint4*>(dA + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
-          }
+          for (int i = 0; i < BM * 8 / THREADS; i++) *reinterpret_cast<uint4*>(dA + soff[i]) = u8x8_to_f16x8(raw[j][i]);
           cp_async_wait<0>();
           fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
           __syncthreads();
@@ -272,13 +286,14 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
   } else {
     // bf16 activations: A and W tiles are straight 16-byte copies, so they go global -> shared asynchronously (LDGSTS),
     // STAGES - 1 k-blocks ahead of the MMAs; no registers, no per-k-block latency exposure.
+    const __nv_bfloat16* act = reinterpret_cast<const __nv_bfloat16*>(a.A);
     auto copy_stage = [&](int kb) {
       const uint32_t dA = smem_u32(sA + (kb % STAGES) * BM * 128);
+      const int koff = a_kb_offset<MODE>(a, kb);
 #pragma unroll
       for (int i = 0; i < BM * 8 / THREADS; i++) {
-        const int c = i * THREADS + tid, row = c >> 3, ch = c & 7, r = m0 + row;
-        const bool valid = r < a.M;
-        cp_async16(dA + row * 128 + ((ch ^ (row & 7)) << 4), valid ? a_chunk_ptr<MODE>(a, r, kb, ch) : a.A, valid);
+        const bool valid = rbase[i] >= 0;
+        cp_async16(dA + soff[i], valid ? act + rbase[i] + koff : act, valid);
       }
       copy_w(kb);
     };
@@ -372,6 +387,29 @@ static uint16_t f2bf(float f) {  // round to nearest even
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
+}
+
+static uint16_t f2h(float f) {  // fp32 -> fp16, round to nearest even (conv1 weights; magnitudes far inside the normal range)
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const int32_t e = (int32_t)((u >> 23) & 0xff) - 127 + 15;
+  uint32_t m = u & 0x7fffffu;
+  if (((u >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (m ? 0x200u : 0));
+  if (e >= 31) return (uint16_t)(sign | 0x7c00u);
+  if (e <= 0) {  // subnormal or zero
+    if (e < -10) return (uint16_t)sign;
+    m |= 0x800000u;
+    const int shift = 14 - e;
+    uint32_t h = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1))) h++;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) h++;
+  return (uint16_t)(sign | h);
 }
 
 struct Shape {
@@ -517,7 +555,7 @@ extern "C" int32_t grp_set_params(grp_policy* p, const float* host, int64_t coun
     std::vector<uint16_t> h;
     // conv1 [32][cin][8][8]: K order (c, ky, kx) is torch's own
     h.resize(32 * (size_t)s.cin * 64);
-    for (size_t i = 0; i < h.size(); i++) h[i] = f2bf(P[L.c1w + i]);
+    for (size_t i = 0; i < h.size(); i++) h[i] = f2h(P[L.c1w + i]);  // fp16: the uint8 pixels convert to fp16 exactly and cheaply
     upload_bf16(p->w1, h);
     // conv2 [64][32][4][4] -> [64][(ky, kx, c)]
     h.assign(64 * 512, 0);
