@@ -38,7 +38,7 @@ enum Epi { EPI_RELU = 0, EPI_FEATURES = 1, EPI_HEAD = 2 };
 
 constexpr int BM = 128;      // rows of A per CTA = TMEM lanes = UMMA M
 constexpr int BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int STAGES = 3;
+__host__ __device__ constexpr int stages_of(int mode) { return mode >= 0 ? 3 : 3; }
 constexpr int THREADS = 128;
 constexpr int FEAT_LD = 576;  // 512 CNN features + 2 direct features, zero padded to a multiple of BK
 constexpr int HEAD_N = 16;    // mu rows 0..A-1, log_std rows 8..8+A-1
@@ -180,11 +180,12 @@ __device__ __forceinline__ uint4 u8x8_to_f16x8(uint2 raw) {
 
 template <int BN>
 __host__ __device__ constexpr int tmem_cols() { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256; }
-template <int BN>
-__host__ __device__ constexpr size_t layer_smem_bytes() { return (size_t)STAGES * (BM * 128 + BN * 128) + 1024; }
+template <int MODE, int BN>
+__host__ __device__ constexpr size_t layer_smem_bytes() { return (size_t)stages_of(MODE) * (BM * 128 + BN * 128) + 1024; }
 
 template <int MODE, int BN, int EPI>
 __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
+  constexpr int STAGES = stages_of(MODE);
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_stage[STAGES];
   __shared__ uint64_t bar_done;
@@ -235,7 +236,9 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
   int rbase[BM * 8 / THREADS], soff[BM * 8 / THREADS];
 #pragma unroll
   for (int i = 0; i < BM * 8 / THREADS; i++) {
-    const int c = i * THREADS + tid, row = c >> 3, ch = c & 7;
+    // bf16 layers: 8 consecutive threads copy the 8 chunks (128 contiguous bytes) of one row.  conv1: one thread per row and
+    // chunk i = kernel row i, so a warp's 4-byte loads walk along an image row (2-3 cache lines per request instead of 8).
+    const int c = i * THREADS + tid, row = MODE == CONV1 ? tid : c >> 3, ch = MODE == CONV1 ? i : c & 7;
     rbase[i] = a_row_base<MODE>(a, m0 + row, ch);
     soff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
   }
@@ -513,7 +516,7 @@ extern "C" grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t he
     p->h2 = palloc<__nv_bfloat16>(p.get(), N * 256);
     p->mu = palloc<float>(p.get(), N * s.adim);
     p->log_std = palloc<float>(p.get(), N * s.adim);
-#define SET_SMEM(M_, BN_, E_) CU(cudaFuncSetAttribute(k_layer<M_, BN_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer_smem_bytes<BN_>()))
+#define SET_SMEM(M_, BN_, E_) CU(cudaFuncSetAttribute(k_layer<M_, BN_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer_smem_bytes<M_, BN_>()))
     SET_SMEM(CONV1, 32, EPI_RELU);
     SET_SMEM(CONV2, 64, EPI_RELU);
     SET_SMEM(CONV3, 64, EPI_RELU);
@@ -623,7 +626,7 @@ extern "C" int32_t grp_get_params(const grp_policy* p, float* host, int64_t coun
 template <int MODE, int BN, int EPI>
 static void launch_layer(grp_policy* p, const LayerArgs& a, int n_total, cudaStream_t st) {
   dim3 grid((a.M + BM - 1) / BM, n_total / BN);
-  k_layer<MODE, BN, EPI><<<grid, THREADS, layer_smem_bytes<BN>(), st>>>(a);
+  k_layer<MODE, BN, EPI><<<grid, THREADS, layer_smem_bytes<MODE, BN>(), st>>>(a);
   CU(cudaGetLastError());
   p->launches++;
 }
