@@ -363,7 +363,11 @@ struct SimBuffers {
   float* render_state;  // [N][RS_STRIDE]
   float* reset_record;  // [ST_STRIDE] state + [IN_STRIDE] info + [RS_STRIDE] render state of a freshly reset environment
   float* debug;         // [N][DEBUG_STRIDE]
-  int* queue;           // [0] work-queue counter, [1..2] bucket counters of the longest-first order
+  int* queue;           // [0] work-queue counter, [1..2] bucket counters of the longest-first order, [3] finished environments,
+                        // [4] observation tickets handed out, [5] blocks that left the fused kernel
+  int* done_list;       // [N] environment ids in the order their agent steps finished (-1 = not yet); fused observation phase
+  int* sm_phys;         // [256] per SM: blocks of the fused kernel still in their physics phase (the observation phase yields to them)
+  unsigned long long* tstamp;  // [0] first block start, [1] last physics-phase end (globaltimer ns), [2] sum of ([1]-[0]), [3] launches
   int* order;           // [N] environment ids, expected-long agent steps first (k_order_envs); identity for the other kernels
   const float4* hull;
   const int* adj;

@@ -11,6 +11,7 @@
 // ragged trip counts only cost idle warps inside a round, never idle rounds.
 #pragma once
 #include "env_kernels.cuh"
+#include "render_kernels.cuh"
 
 namespace grs {
 
@@ -180,7 +181,11 @@ __device__ __noinline__ void env_writeback(const DevModel& m, const EnvCfg& c, c
   } else {
     store_state(w, t.f, st, lane);
   }
+  // publish: this environment's results are complete (release: every lane fences its own stores, then lane 0 appends the
+  // environment to the finished list that the observation phase consumes in order)
+  __threadfence();
   __syncwarp();
+  if (lane == 0) atomicExch(s.done_list + atomicAdd(s.queue + 3, 1), env);
 }
 
 // Longest-first queue order.  An agent step is a chain of dependent substeps whose length is ragged and
@@ -195,6 +200,7 @@ __global__ void k_order_envs(SimBuffers s, const float* __restrict__ actions, in
   const bool is_long = (oc > 0.f && !open) || (oc < 0.f && open);
   const int pos = is_long ? atomicAdd(s.queue + 1, 1) : s.n - 1 - atomicAdd(s.queue + 2, 1);
   s.order[pos] = env;
+  s.done_list[env] = -1;
 }
 
 #ifndef LS_BARRIERS
@@ -204,8 +210,22 @@ constexpr int LS_MAX_THREADS = 640;  // 20 warps: one block per SM (20 x 10.3 KB
 
 // TIMING = true: per-stage clock64 bookkeeping (sum over warps vs. per-round block maximum) into s.debug — a development
 // aid behind GRS_STEP_TIMING=1 that quantifies what the block barriers cost; the production instantiation carries none of it.
-template <bool TIMING>
-__global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s, EnvCfg c, const float* __restrict__ actions, int adim) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// FUSED = true: a block whose physics work is exhausted goes on to build observations (render_phase) instead of exiting, so
+// the rasteriser fills the SMs that idle while the longest substep chains finish.  Needs blockDim.x == RTHREADS.
+template <bool TIMING, bool FUSED>
+__global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s, EnvCfg c, const float* __restrict__ actions, int adim, RenderScene sc, ObsArgs oa) {
+  unsigned smid = 0;
+  if (FUSED && threadIdx.x == 0) {
+    atomicMin(s.tstamp, global_ns());
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    atomicAdd(s.sm_phys + (smid & 255), 1);
+  }
   const DevModel& m = stage_model(s.model);
   WS& w = my_ws();
   const int lane = threadIdx.x & 31;
@@ -271,6 +291,21 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
     LS_T0();
     if (pos) collision(m, w, s.hull, s.adj, lane);
     LS_T1(6);
+  }
+  if (FUSED) {
+    if (threadIdx.x == 0) {  // end of this block's physics phase
+      atomicMax(s.tstamp + 1, global_ns());
+      atomicSub(s.sm_phys + (smid & 255), 1);
+    }
+    render_phase(sc, oa, s, grs_smem, s.sm_phys + (smid & 255));
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(s.queue + 5, 1) == (int)gridDim.x - 1) {  // last block out: account the physics phase of this launch
+        const unsigned long long t0 = atomicAdd(s.tstamp, 0ull), t1 = atomicAdd(s.tstamp + 1, 0ull);
+        s.tstamp[2] += t1 - t0; s.tstamp[3] += 1;
+        s.tstamp[0] = ~0ull; s.tstamp[1] = 0;
+      }
+    }
   }
   if (TIMING) {
     __syncthreads();

@@ -62,7 +62,9 @@ struct grs_sim {
   // lock-step step kernel geometry (GRS_STEP_WARPS warps per block; 0 selects the sequential kernel)
   int ls_warps = 8, ls_grid = 0;
   bool ls_timing = false;
+  bool fused_render = false;  // observation phase inside the step kernel (env_lockstep.cuh : render_phase)
   size_t ls_smem = 0;
+  ObsArgs obs_args{};
 };
 
 template <class T>
@@ -100,7 +102,7 @@ static void harvest_events(grs_sim* s) {
   s->ev_n = 0;
 }
 
-static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, 4 * sizeof(int), st)); }
+static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, 8 * sizeof(int), st)); }
 
 extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs_config* cfg_in, int32_t device) {
   grs_sim* raw = nullptr;
@@ -144,7 +146,11 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     b.render_state = dalloc<float>(s.get(), N * RS_STRIDE);
     b.reset_record = dalloc<float>(s.get(), ST_STRIDE + IN_STRIDE + RS_STRIDE);
     b.debug = dalloc<float>(s.get(), N * DEBUG_STRIDE);
-    b.queue = dalloc<int>(s.get(), 4);
+    b.queue = dalloc<int>(s.get(), 8);
+    b.done_list = dalloc<int>(s.get(), N);
+    b.sm_phys = dalloc<int>(s.get(), 256);
+    b.tstamp = dalloc<unsigned long long>(s.get(), 4);
+    { const unsigned long long init[4] = {~0ull, 0, 0, 0}; CU(cudaMemcpy(b.tstamp, init, sizeof init, cudaMemcpyHostToDevice)); }
     b.ls_mask = 22;
     if (const char* e = getenv("GRS_LS_MASK")) b.ls_mask = atoi(e);
     b.order = dalloc<int>(s.get(), N);
@@ -177,11 +183,16 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     if (const char* e = getenv("GRS_STEP_WARPS")) s->ls_warps = std::max(0, std::min(20, atoi(e)));
     if (s->ls_warps > 0) {
       s->ls_smem = (sizeof(DevModel) + 15) / 16 * 16 + (size_t)s->ls_warps * sizeof(WS);
-      CU(cudaFuncSetAttribute(k_env_step_ls<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
-      CU(cudaFuncSetAttribute(k_env_step_ls<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
       s->ls_timing = getenv("GRS_STEP_TIMING") != nullptr;
+      // the observation phase needs RTHREADS-wide blocks and the observation tile in the block's shared memory
+      s->fused_render = !s->ls_timing && s->ls_warps * 32 == RTHREADS && s->ls_smem >= render_phase_smem_bytes() && cfg.width <= TILE && cfg.height <= TILE;
+      if (const char* e = getenv("GRS_FUSED_RENDER")) s->fused_render = s->fused_render && atoi(e) != 0;
+      CU(cudaFuncSetAttribute(k_env_step_ls<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
+      CU(cudaFuncSetAttribute(k_env_step_ls<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
+      CU(cudaFuncSetAttribute(k_env_step_ls<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
       int ls_per_sm = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, k_env_step_ls<false>, s->ls_warps * 32, s->ls_smem));
+      if (s->fused_render) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, k_env_step_ls<false, true>, s->ls_warps * 32, s->ls_smem));
+      else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, k_env_step_ls<false, false>, s->ls_warps * 32, s->ls_smem));
       if (ls_per_sm < 1) throw std::runtime_error("lock-step step kernel does not fit on this device");
       s->ls_grid = std::min((num_envs + s->ls_warps - 1) / s->ls_warps, ls_per_sm * nsm);
     }
@@ -191,8 +202,14 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     k_make_reset_record<<<1, 32, s->smem, s->stream>>>(s->b, s->ecfg);
     CU(cudaGetLastError());
     s->launches++;
-    launch_render_obs(s->scene, s->b.reset_record + ST_STRIDE + IN_STRIDE, s->b.reset_record + ST_STRIDE, nullptr, nullptr, s->d_reset_obs, nullptr, nullptr,
-                      s->d_hist + N * 512, nullptr, 1, s->C, s->H, s->W, s->hm.cam_fovy[e.obs_cam], 0, 0, s->stream);
+    ObsArgs& oa = s->obs_args;
+    oa.obs = s->d_obs; oa.terminal_obs = s->d_terminal_obs; oa.reset_obs = s->d_reset_obs; oa.hist_prev = s->d_hist; oa.hist_reset = s->d_hist + N * 512;
+    oa.C = s->C; oa.H = s->H; oa.W = s->W; oa.fovy = (float)s->hm.cam_fovy[e.obs_cam]; oa.auto_reset = e.auto_reset; oa.im_reward = e.im_reward;
+    {
+      ObsArgs r = oa;  // the reset image: one environment, no previous histograms (they go to hist_reset), no reward
+      r.obs = s->d_reset_obs; r.terminal_obs = nullptr; r.reset_obs = nullptr; r.hist_prev = nullptr; r.auto_reset = 0; r.im_reward = 0;
+      launch_render_obs(s->scene, r, s->b.reset_record + ST_STRIDE + IN_STRIDE, s->b.reset_record + ST_STRIDE, nullptr, nullptr, 1, s->stream);
+    }
     s->launches++;
     CU(cudaStreamSynchronize(s->stream));
     if (grs_reset(s.get(), nullptr, nullptr) != 0) throw std::runtime_error(g_err);
@@ -254,15 +271,16 @@ extern "C" int32_t grs_step(grs_sim* s, const float* actions_dev, void* stream) 
     if (s->ev_n == grs_sim::NEV) harvest_events(s);
     CU(cudaEventRecord(s->ev0[s->ev_n], st));
     if (s->ls_warps > 0) { k_order_envs<<<(s->n + 255) / 256, 256, 0, st>>>(s->b, actions_dev, s->adim); s->launches++; }
-    if (s->ls_warps > 0 && s->ls_timing) k_env_step_ls<true><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
-    else if (s->ls_warps > 0) k_env_step_ls<false><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
+    const bool fused = s->ls_warps > 0 && s->fused_render;
+    if (fused) k_env_step_ls<false, true><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim, s->scene, s->obs_args);
+    else if (s->ls_warps > 0 && s->ls_timing) k_env_step_ls<true, false><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim, s->scene, s->obs_args);
+    else if (s->ls_warps > 0) k_env_step_ls<false, false><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim, s->scene, s->obs_args);
     else k_env_step<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, s->ecfg, actions_dev, s->adim);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev1[s->ev_n], st));
     s->ev_n++;
-    launch_render_obs(s->scene, s->b.render_state, s->b.info, s->b.done, s->b.reward, s->d_obs, s->d_terminal_obs, s->d_reset_obs, s->d_hist,
-                      s->d_hist + (size_t)s->n * 512, s->n, s->C, s->H, s->W, s->hm.cam_fovy[s->ecfg.obs_cam], s->ecfg.auto_reset, s->ecfg.im_reward, st);
-    s->launches += 2;
+    if (!fused) { launch_render_obs(s->scene, s->obs_args, s->b.render_state, s->b.info, s->b.done, s->b.reward, s->n, st); s->launches++; }
+    s->launches += 1;
     return 0;
   } catch (const std::exception& e) { return fail(e.what()); }
 }
@@ -560,6 +578,14 @@ extern "C" float grs_step_kernel_ms(grs_sim* s, int32_t reset_counters) {
   cudaSetDevice(s->device);
   harvest_events(s);
   float avg = s->ms_cnt ? (float)(s->ms_sum / s->ms_cnt) : 0.0f;
+  if (s->fused_render && s->ls_warps > 0) {
+    // fused kernel: the physics phase is timed on the device (globaltimer: first block start -> last block leaving the
+    // substep loop, accumulated by the last block of every launch); the events above cover physics + observation phases
+    unsigned long long t[4] = {0, 0, 0, 0};
+    if (cudaStreamSynchronize(s->stream) == cudaSuccess && cudaMemcpy(t, s->b.tstamp, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess && t[3])
+      avg = (float)((double)t[2] / (double)t[3] * 1e-6);
+    if (reset_counters) cudaMemset(s->b.tstamp + 2, 0, 2 * sizeof(unsigned long long));
+  }
   if (reset_counters) { s->ms_sum = 0; s->ms_cnt = 0; }
   return avg;
 }

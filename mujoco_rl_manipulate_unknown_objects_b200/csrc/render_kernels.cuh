@@ -378,20 +378,33 @@ __device__ __forceinline__ float block_reduce(float v, float* red, int op /*0 su
   return red[RTHREADS / 32];
 }
 
-// Observation kernel: one block per environment (the observation is a single tile, W,H <= 64).
-//   info      : per-env info rows (grasp / pheromone scalars for the pad channel)
-//   done      : per-env done flags of the step just taken (NULL for the reset image)
-//   obs       : [n][C][H][W] uint8; terminal_obs likewise; reset_obs [C][H][W]
-//   hist_prev : [n][2][256] float histograms (grey, depth) of each env's previous observation; hist_reset the reset image's
-__global__ void __launch_bounds__(RTHREADS) k_render_obs(RenderScene sc, const float* __restrict__ render_state, const float* __restrict__ info, int info_stride,
-                                                        const unsigned char* __restrict__ done, float* __restrict__ reward, unsigned char* __restrict__ obs,
-                                                        unsigned char* __restrict__ terminal_obs, const unsigned char* __restrict__ reset_obs, float* __restrict__ hist_prev,
-                                                        float* __restrict__ hist_reset, int C, int H, int W, float fovy, int auto_reset, int im_reward) {
-  extern __shared__ __align__(16) unsigned char rsm[];
-  TileShared& sh = *reinterpret_cast<TileShared*>(rsm);
-  unsigned* rgb8 = reinterpret_cast<unsigned*>(rsm + sizeof(TileShared));
-  const int env = blockIdx.x, tid = threadIdx.x;
-  render_tile(sc, render_state + (size_t)env * RS_STRIDE, sh, rgb8, W, H, 0, 0, W, H, fovy);
+// Everything the observation builder needs besides the per-step simulator buffers.
+struct ObsArgs {
+  unsigned char* obs;           // [n][C][H][W] uint8
+  unsigned char* terminal_obs;  // likewise (SB3 terminal observation of environments that finished an episode)
+  const unsigned char* reset_obs;  // [C][H][W] observation of a freshly reset environment
+  float* hist_prev;             // [n][2][256] float histograms (grey, depth) of each env's previous observation
+  float* hist_reset;            // the reset image's histograms
+  int C, H, W;
+  float fovy;
+  int auto_reset, im_reward;
+};
+
+// Observation of ONE environment by one block of RTHREADS threads (the observation is a single tile, W,H <= 64):
+// rasterise + shade (render_tile), transform_depth, uint8 CHW packing with the two scalar channels, histograms, intrinsic
+// reward, SB3 terminal-observation / reset-observation swap.
+//   rs       : this env's render state (geom poses + camera), any address space
+//   pad0/1   : grasp / pheromone scalars of the pad channel;  is_done : done flag of the step just taken
+//   reward   : per-env reward array (the intrinsic term is added in place), or NULL
+__device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsArgs& o, const float* rs, int env, unsigned char pad0, unsigned char pad1,
+                                               bool is_done, float* reward, TileShared& sh, unsigned* rgb8) {
+  const int tid = threadIdx.x, C = o.C, H = o.H, W = o.W, auto_reset = o.auto_reset, im_reward = o.im_reward;
+  unsigned char* obs = o.obs;
+  unsigned char* terminal_obs = o.terminal_obs;
+  const unsigned char* reset_obs = o.reset_obs;
+  float* hist_prev = o.hist_prev;
+  float* hist_reset = o.hist_reset;
+  render_tile(sc, rs, sh, rgb8, W, H, 0, 0, W, H, o.fovy);
   const int npix = W * H;
   // transform_depth (utils.py:11-19): d -= min(d); d /= 2*mean(d[d <= 1]); 255*clip(d, 0, 1)
   float mn = 3.0e38f;
@@ -407,10 +420,7 @@ __global__ void __launch_bounds__(RTHREADS) k_render_obs(RenderScene sc, const f
   const float denom = 2.0f * (sm / cnt);  // cnt >= 1: the minimum pixel itself
   for (int i = tid; i < 512; i += RTHREADS) (&sh.hist[0][0])[i] = 0;
   __syncthreads();
-  const bool is_done = done ? done[env] != 0 : false;
   unsigned char* dst = (is_done && auto_reset) ? terminal_obs + (size_t)env * C * npix : obs + (size_t)env * C * npix;
-  const float* inf = info + (size_t)env * info_stride;
-  const unsigned char pad0 = (unsigned char)inf[IN_GRASP], pad1 = (unsigned char)inf[IN_PHEROMONE];
   for (int i = tid; i < npix; i += RTHREADS) {
     int y = i / W, x = i - y * W;
     unsigned c = rgb8[y * TILE + x];
@@ -440,7 +450,7 @@ __global__ void __launch_bounds__(RTHREADS) k_render_obs(RenderScene sc, const f
     }
     kl_g = block_reduce(kl_g, sh.red, 0);
     kl_d = block_reduce(kl_d, sh.red, 0);
-    if (tid == 0) reward[env] += C == 5 ? 0.5f * (kl_g + kl_d) : kl_g;
+    if (tid == 0) reward[env] = __ldcg(reward + env) + (C == 5 ? 0.5f * (kl_g + kl_d) : kl_g);
   }
   __syncthreads();
   if (is_done && auto_reset) {
@@ -456,20 +466,70 @@ __global__ void __launch_bounds__(RTHREADS) k_render_obs(RenderScene sc, const f
   }
 }
 
+// Standalone observation kernel: one block per environment.  info: per-env info rows; done: per-env done flags (NULL for
+// the reset image).  Used for the reset image, the sequential step kernel and GRS_FUSED_RENDER=0.
+__global__ void __launch_bounds__(RTHREADS) k_render_obs(RenderScene sc, ObsArgs o, const float* __restrict__ render_state, const float* __restrict__ info, int info_stride,
+                                                        const unsigned char* __restrict__ done, float* __restrict__ reward) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  TileShared& sh = *reinterpret_cast<TileShared*>(rsm);
+  unsigned* rgb8 = reinterpret_cast<unsigned*>(rsm + sizeof(TileShared));
+  const int env = blockIdx.x;
+  const float* inf = info + (size_t)env * info_stride;
+  render_obs_env(sc, o, render_state + (size_t)env * RS_STRIDE, env, (unsigned char)inf[IN_GRASP], (unsigned char)inf[IN_PHEROMONE], done ? done[env] != 0 : false, reward, sh, rgb8);
+}
+
 inline size_t render_smem_bytes() { return sizeof(TileShared) + TILE * TILE * sizeof(unsigned); }
+inline size_t render_phase_smem_bytes() { return render_smem_bytes() + RS_STRIDE * sizeof(float); }
+
+// Observation phase of the fused step kernel (env_lockstep.cuh).  A block whose physics work is exhausted turns into an
+// observation builder: it takes tickets from a global counter and renders environments in the order in which their
+// agent steps finished (s.done_list, published by env_writeback with release semantics), so the rasteriser runs on SMs
+// that would otherwise idle while the longest substep chains of the batch complete.  Requires blockDim.x == RTHREADS and
+// every block of the grid resident (persistent grid), which the launch code guarantees.  Inputs written by other SMs
+// during this same kernel are read through L2 (ld.cg): L1 is not coherent.  sm_busy: see below.
+__device__ __forceinline__ void render_phase(const RenderScene& sc, const ObsArgs& o, const SimBuffers& s, unsigned char* smem, int* sm_busy) {
+  TileShared& sh = *reinterpret_cast<TileShared*>(smem);
+  unsigned* rgb8 = reinterpret_cast<unsigned*>(smem + sizeof(TileShared));
+  float* rs = reinterpret_cast<float*>(smem + sizeof(TileShared) + TILE * TILE * sizeof(unsigned));
+  __shared__ int cur_env;
+  const int tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      // yield to a sibling block of this SM that is still integrating substeps: the kernel's duration is the longest substep
+      // chain, and rasterising next to it would slow exactly that chain (sm_busy is only meaningful to thread 0's SM)
+      while (*reinterpret_cast<volatile int*>(sm_busy) > 0) __nanosleep(2000);
+      const int ticket = atomicAdd(s.queue + 4, 1);
+      int env = -1;
+      if (ticket < s.n) {
+        volatile int* slot = s.done_list + ticket;
+        while ((env = *slot) < 0) __nanosleep(200);
+        __threadfence();
+      }
+      cur_env = env;
+    }
+    __syncthreads();
+    const int env = cur_env;
+    if (env < 0) break;
+    if (tid < RS_STRIDE) rs[tid] = __ldcg(s.render_state + (size_t)env * RS_STRIDE + tid);
+    const float* inf = s.info + (size_t)env * IN_STRIDE;
+    const unsigned char pad0 = (unsigned char)__ldcg(inf + IN_GRASP), pad1 = (unsigned char)__ldcg(inf + IN_PHEROMONE);
+    const bool is_done = __ldcg(s.done + env) != 0;
+    __syncthreads();
+    render_obs_env(sc, o, rs, env, pad0, pad1, is_done, s.reward, sh, rgb8);
+  }
+}
 
 // obs == reset image path: done = NULL, n = 1, hist_prev = NULL -> histograms go to hist_reset
-inline void launch_render_obs(const RenderScene& sc, const float* render_state, const float* info, const unsigned char* done, float* reward, unsigned char* obs,
-                              unsigned char* terminal_obs, const unsigned char* reset_obs, float* hist_prev, float* hist_reset, int n, int C, int H, int W, double fovy,
-                              int auto_reset, int im_reward, cudaStream_t st) {
-  if (W > TILE || H > TILE) throw std::runtime_error("observation size above 64x64 is not supported by the fused observation kernel");
+inline void launch_render_obs(const RenderScene& sc, const ObsArgs& o, const float* render_state, const float* info, const unsigned char* done, float* reward, int n,
+                              cudaStream_t st) {
+  if (o.W > TILE || o.H > TILE) throw std::runtime_error("observation size above 64x64 is not supported by the fused observation kernel");
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(k_render_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_smem_bytes()) != cudaSuccess) throw std::runtime_error("cudaFuncSetAttribute(k_render_obs)");
     attr = true;
   }
-  k_render_obs<<<n, RTHREADS, render_smem_bytes(), st>>>(sc, render_state, info, IN_STRIDE, done, reward, obs, terminal_obs, reset_obs, hist_prev, hist_reset, C, H, W,
-                                                         (float)fovy, auto_reset, im_reward);
+  k_render_obs<<<n, RTHREADS, render_smem_bytes(), st>>>(sc, o, render_state, info, IN_STRIDE, done, reward);
   if (cudaGetLastError() != cudaSuccess) throw std::runtime_error("k_render_obs launch failed");
 }
 
