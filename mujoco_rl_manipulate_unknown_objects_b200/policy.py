@@ -103,6 +103,18 @@ class GripperPolicy:
         flat = np.concatenate(flat)
         self._check(self._lib.grp_set_params(self._h, C.c_void_p(flat.ctypes.data), flat.size))
 
+    def load_sb3_zip(self, path):
+        """Loads the actor of a stable-baselines3 SAC archive (reference eval_agent.py:34-48: `SAC.load(best_model, ...)`)."""
+        from .sb3_io import read_sb3_zip
+        sd, data = read_sb3_zip(path)
+        self.load_state_dict(sd, prefix="actor.")
+        return data
+
+    def save_sb3_zip(self, path, data=None):
+        """Writes the actor's parameters as a stable-baselines3 archive (policy.pth with 'actor.*' names)."""
+        from .sb3_io import write_sb3_zip
+        return write_sb3_zip(path, self.state_dict(), data=data)
+
     def state_dict(self):
         n = self._lib.grp_num_params(self._h)
         flat = np.zeros(n, np.float32)

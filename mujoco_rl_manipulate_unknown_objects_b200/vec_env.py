@@ -128,10 +128,16 @@ class BatchedRobotVecEnv(_VecEnvBase):
 
     metadata = {"render.modes": ["rgb_array", "depth_array"]}
 
-    def __init__(self, config=None, num_envs=1, device=0, **overrides):
+    def __init__(self, config=None, num_envs=1, device=0, monitor_file=None, **overrides):
+        """monitor_file: directory or file prefix of a stable-baselines3 `monitor.csv` (train_agent.py:22 wraps the
+        environment in `Monitor(env, log_dir)`); one `r,l,t` row is appended per finished episode."""
         if config is None:
             config = make_config(**overrides)
         self.config = config
+        self._monitor = None
+        if monitor_file is not None:
+            from .sb3_io import MonitorWriter
+            self._monitor = MonitorWriter(monitor_file)
         self.sim = GripperSim(config, num_envs=num_envs, device=device, auto_reset=True)
         self.observation_space, self.action_space = make_spaces(config)
         if _VecEnvBase is not object:  # pragma: no cover
@@ -169,6 +175,8 @@ class BatchedRobotVecEnv(_VecEnvBase):
         self._actions = None
         dones = self._h_done.astype(bool)
         infos = LazyInfos(self._h_info.copy(), dones, self._h_tobs.copy() if dones.any() else None, self.target_direction, self._t_start)
+        if self._monitor is not None and dones.any():
+            self._monitor.write_step(dones, infos)
         return self._obs_dict(), self._h_rew.copy(), dones, infos
 
     def step(self, actions):
@@ -185,6 +193,8 @@ class BatchedRobotVecEnv(_VecEnvBase):
         return {"observation": s.obs, "achieved_goal": s.achieved_goal, "desired_goal": s.desired_goal}, s.reward, s.done, s.info
 
     def close(self):
+        if self._monitor is not None:
+            self._monitor.close()
         self.sim.close()
 
     def seed(self, seed=None):
