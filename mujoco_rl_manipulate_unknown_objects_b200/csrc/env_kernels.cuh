@@ -370,6 +370,8 @@ struct SimBuffers {
   unsigned long long* tstamp;  // [0] first block start, [1] last physics-phase end (globaltimer ns), [2] sum of ([1]-[0]), [3] launches
   int* order;           // [N] environment ids, expected-long agent steps first (k_order_envs); identity for the other kernels
   const float4* hull;
+  int hull_count;       // float4 entries behind `hull`; the lock-step kernel copies them to shared memory when hull_smem is set
+  int hull_smem;
   const int* adj;
   const DevModel* model;
   int n;

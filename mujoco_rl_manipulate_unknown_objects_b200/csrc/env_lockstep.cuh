@@ -229,6 +229,15 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
   const DevModel& m = stage_model(s.model);
   WS& w = my_ws();
   const int lane = threadIdx.x & 31;
+  // convex-hull vertices of every geom -> shared memory (behind the workspaces): the support scans of the collision stage
+  // then cost shared-memory latency instead of L1/L2 round trips (they were half of that stage's stall samples)
+  const float4* hull = s.hull;
+  if (s.hull_smem) {
+    float4* hs = reinterpret_cast<float4*>(grs_smem + (sizeof(DevModel) + 15) / 16 * 16 + (size_t)(blockDim.x >> 5) * sizeof(WS));
+    for (int i = threadIdx.x; i < s.hull_count; i += blockDim.x) hs[i] = s.hull[i];
+    hull = hs;
+    __syncthreads();
+  }
   __shared__ unsigned long long t_sum[8], t_max[8], t_round[8];
   __shared__ unsigned long long t_rounds;
   if (TIMING) { if (threadIdx.x < 8) { t_sum[threadIdx.x] = 0; t_max[threadIdx.x] = 0; t_round[threadIdx.x] = 0; } if (threadIdx.x == 0) t_rounds = 0; __syncthreads(); }
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
     LS_T1(5);
     if (s.ls_mask & 16) __syncthreads();
     LS_T0();
-    if (pos) collision(m, w, s.hull, s.adj, lane);
+    if (pos) collision(m, w, hull, s.adj, lane);
     LS_T1(6);
   }
   if (FUSED) {

@@ -137,6 +137,7 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     const size_t N = num_envs;
     SimBuffers& b = s->b;
     b.n = num_envs; b.model = s->d_model; b.hull = s->d_hull; b.adj = s->d_adj;
+    b.hull_count = (int)(hv.size() / 4); b.hull_smem = 0;
     b.state = dalloc<float>(s.get(), N * ST_STRIDE);
     b.info = dalloc<float>(s.get(), N * IN_STRIDE);
     b.reward = dalloc<float>(s.get(), N);
@@ -183,6 +184,12 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     if (const char* e = getenv("GRS_STEP_WARPS")) s->ls_warps = std::max(0, std::min(20, atoi(e)));
     if (s->ls_warps > 0) {
       s->ls_smem = (sizeof(DevModel) + 15) / 16 * 16 + (size_t)s->ls_warps * sizeof(WS);
+      {
+        // hull vertices in shared memory when two blocks per SM still fit (227 KB per block, 228 KB per SM, 1 KB reserved each)
+        const size_t with_hull = s->ls_smem + (size_t)s->b.hull_count * sizeof(float4);
+        const bool want = getenv("GRS_HULL_SMEM") ? atoi(getenv("GRS_HULL_SMEM")) != 0 : true;
+        if (want && 2 * (with_hull + 1024) <= 228 * 1024) { s->ls_smem = with_hull; s->b.hull_smem = 1; }
+      }
       s->ls_timing = getenv("GRS_STEP_TIMING") != nullptr;
       // the observation phase needs RTHREADS-wide blocks and the observation tile in the block's shared memory
       s->fused_render = !s->ls_timing && s->ls_warps * 32 == RTHREADS && s->ls_smem >= render_phase_smem_bytes() && cfg.width <= TILE && cfg.height <= TILE;

@@ -402,7 +402,7 @@ __device__ __noinline__ int support_geom(const DevModel& m, const WS& w, const f
   int bi = 0;
 #pragma unroll 2
   for (int i = lane; i < n; i += 32) {
-    float4 p = __ldg(v + i);
+    float4 p = v[i];  // generic load: the lock-step kernel stages the hulls in shared memory
     float s = p.x * l[0] + p.y * l[1] + p.z * l[2];
     if (s > best) { best = s; bi = i; }
   }
@@ -412,7 +412,7 @@ __device__ __noinline__ int support_geom(const DevModel& m, const WS& w, const f
     int oi = __shfl_xor_sync(FULL, bi, o);
     if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
-  float4 p = __ldg(v + bi);
+  float4 p = v[bi];
   float pv[3] = {p.x, p.y, p.z}, t[3];
   mulmat3vec(t, R, pv);
   out[0] = w.gpos[g][0] + t[0]; out[1] = w.gpos[g][1] + t[1]; out[2] = w.gpos[g][2] + t[2];
@@ -667,7 +667,7 @@ __device__ __noinline__ void collision(const DevModel& m, WS& w, const float4* h
       const float4* hvg = hv + m.geom_hvadr[g2];
       for (int e = e0; e < e1 && cnt < 3; e++) {
         int nb = __ldg(ga + nvert + 1 + e);
-        float4 q = __ldg(hvg + nb);
+        float4 q = hvg[nb];
         float qv[3] = {q.x, q.y, q.z}, t[3];
         mulmat3vec(t, w.gmat[g2], qv);
         for (int k = 0; k < 3; k++) { v[k] = w.gpos[g2][k] + t[k]; dif[k] = v[k] - w.gpos[g1][k]; }
