@@ -21,6 +21,9 @@ for i in range(40):
 a = np.concatenate([r["a"] for r in rec]); ns = np.concatenate([r["ns"] for r in rec]); tot = ns.sum(1)
 print("kernel ms per step:", np.round([r["ms"] for r in rec], 1))
 print("per-step max chain:", [int(r["ns"].sum(1).max()) for r in rec])
+print("us per round of the longest chain: mean %.1f  (steps with max<300: %.1f, others: %.1f); mean kernel %.2f ms" % (
+    np.mean([1e3 * r["ms"] / r["ns"].sum(1).max() for r in rec]), np.mean([1e3 * r["ms"] / r["ns"].sum(1).max() for r in rec if r["ns"].sum(1).max() < 300] or [0]),
+    np.mean([1e3 * r["ms"] / r["ns"].sum(1).max() for r in rec if r["ns"].sum(1).max() >= 300] or [0]), np.mean([r["ms"] for r in rec])))
 tn = np.linalg.norm(a[:, :3], axis=1)
 for lo, hi in ((0, .5), (.5, .8), (.8, 1.0), (1.0, 1.2), (1.2, 2)):
     m = (tn >= lo) & (tn < hi)
