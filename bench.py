@@ -171,6 +171,7 @@ def run_ours(args):
     sub_acc = torch.zeros(1, device=dev, dtype=torch.float64)
     done_acc = torch.zeros(1, device=dev, dtype=torch.float64)
     ret_acc = torch.zeros(1, device=dev, dtype=torch.float64)
+    chain_acc = torch.zeros(1, device=dev, dtype=torch.float64)  # sum over steps of the longest substep chain of the batch
     c0, c1 = INFO["NSUB_A"], INFO["NSUB_A"] + 3
     from mujoco_rl_manipulate_unknown_objects_b200.policy import GripperPolicy
     policy = GripperPolicy(max_envs=N, obs_shape=sim.obs_shape, action_dim=sim.action_dim, device=local, seed=args.seed)
@@ -206,7 +207,9 @@ def run_ours(args):
         ev[i][0].record()
         one_step(W + i)
         ev[i][1].record()
-        sub_acc += sim.info[:, c0:c1].sum()
+        nsub = sim.info[:, c0:c1].sum(1)
+        sub_acc += nsub.sum()
+        chain_acc += nsub.max()
         done_acc += sim.done.sum()
         ret_acc += sim.reward.sum()
     barrier()
@@ -234,8 +237,14 @@ def run_ours(args):
     h_obs, h_rew, h_done = pin((N, Cc, H, Wd), torch.uint8), pin((N,), torch.float32), pin((N,), torch.uint8)
     h_ag, h_dg, h_info = pin((N, 2), torch.float32), pin((N, 2), torch.float32), pin((N, INFO["STRIDE"]), torch.float32)
     acts_host = actions[W:].cpu().numpy()
-    KE = max(3, min(K, 20))
+    KE = K
     e2e_sub = 0.0
+    if not args.policy:
+        # replay: same reset state, same warm-up and timed action tapes -> the very trajectories (and substep chains) of the
+        # device-timed region, now through host buffers, so `e2e` and `value` differ only by the copies
+        sim.reset()
+        for i in range(W):
+            one_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(KE):
@@ -247,7 +256,7 @@ def run_ours(args):
     h2d = h_act.nbytes
     d2h = h_obs.nbytes + h_rew.nbytes + h_done.nbytes + h_ag.nbytes + h_dg.nbytes + h_info.nbytes
     # ---- aggregate over ranks: units summed, time = max
-    stats = torch.tensor([sub_acc.item(), float(N * K), done_acc.item(), ret_acc.item(), e2e_sub, float(launches)], device=dev, dtype=torch.float64)
+    stats = torch.tensor([sub_acc.item(), float(N * K), done_acc.item(), ret_acc.item(), e2e_sub, float(launches), chain_acc.item()], device=dev, dtype=torch.float64)
     tmax = torch.tensor([dev_ms, wall * 1e3, e2e_s * 1e3, kernel_ms, pol_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # rollout-statistics reduction: the only collective on this path
@@ -269,7 +278,9 @@ def run_ours(args):
                 "mean_reward_per_transition": stats[3] / transitions, "wall_ms_per_step": tmax[1] / K,
                 "e2e": {"value": stats[4] / (tmax[2] / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": KE,
                         "transitions_per_s": N * KE * world / (tmax[2] / 1e3), "api": "grs_step_host (C-ABI, pinned host buffers)"},
-                "gpu_launches": int(stats[5] // world), "clocks": clk}
+                "gpu_launches": int(stats[5] // world), "clocks": clk,
+                # an agent step is a chain of dependent substeps; the synchronous VecEnv step lasts as long as the batch's longest chain
+                "longest_chain_substeps": stats[6] / world / K, "us_per_substep_of_longest_chain": tmax[3] * 1e3 / max(stats[6] / world / K, 1.0)}
         per_launch_sub = substeps / world / K
         kms = tmax[3]
         peaks = {}
