@@ -295,11 +295,13 @@ def run_ours(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_env_step_bytes_per_launch")
         except Exception:
             pass
-        line["roofline"] = {"bound": "hbm", "kernel": "k_env_step (fused agent step: controller + <=1200 substeps + reward, state on chip)",
+        line["roofline"] = {"bound": "hbm", "kernel": "k_env_step_ls, physics phase (fused agent step: controller + <=1200 substeps + reward, state on chip; "
+                                                      "device-timed: first block start -> last block leaving the substep loop)",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                             "kernel_ms": kms, "bytes_per_substep": BYTES_PER_SUBSTEP, "substeps_per_launch": per_launch_sub,
-                            "note": "fused kernel keeps state on chip: it is FP32-latency bound, not HBM bound (SURVEY.md §8d); "
+                            "note": "fused kernel keeps state on chip: it is latency bound by the batch's longest chain of dependent substeps, not HBM bound "
+                                    "(SURVEY.md §8d, DESIGN.md §3.1; traffic = physics + observation phases of one launch); "
                                     "per-transition accounting (%d B incl. the 20 480 B observation) gives %.1f GB/s over the whole step" % (
                                         BYTES_PER_TRANSITION, transitions / world / K * BYTES_PER_TRANSITION / (tmax[0] / K / 1e3) / 1e9)}
         flop = 2 * (225 * 64 * (sim.obs_shape[0] - 1) * 32 + 36 * 512 * 64 + 16 * 576 * 64 + 1024 * 512 + 514 * 256 + 256 * 256 + 256 * 2 * sim.action_dim)
