@@ -110,7 +110,7 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     if (num_envs <= 0) throw std::runtime_error("num_envs must be positive");
     grs_config cfg;
     if (cfg_in) cfg = *cfg_in; else grs_default_config(&cfg);
-    if (cfg.direction != 0 && cfg.direction != 45) throw std::runtime_error("direction must be 0 or 45 (robot_env.py:30-33)");
+    if (cfg.direction < -360 || cfg.direction > 360) throw std::runtime_error("direction must be an angle in degrees within [-360, 360] (robot_env.py:30-33: 0 and 45 are the reference's cases)");
     if (cfg.width <= 0 || cfg.height <= 0 || cfg.width > 256 || cfg.height > 256) throw std::runtime_error("observation size must be within 1..256");
     if (cfg.max_steps <= 0 || cfg.time_horizon <= 0) throw std::runtime_error("max_steps and time_horizon must be positive");
     int ndev = 0;
@@ -166,7 +166,12 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     e.im_reward = cfg.im_reward; e.auto_reset = cfg.auto_reset; e.full_observation = cfg.full_observation;
     e.obs_cam = 0;
     for (int c = 0; c < s->hm.ncam; c++) if (s->hm.cam_names[c] == "gripper_camera") e.obs_cam = c;  // robot_env.py:281
-    e.dir[0] = 1.0f; e.dir[1] = cfg.direction == 45 ? 1.0f : 0.0f;
+    e.dir[0] = 1.0f; e.dir[1] = cfg.direction == 45 ? 1.0f : 0.0f;  // robot_env.py:30-33: (1, 0) and the un-normalised (1, 1)
+    if (cfg.direction != 0 && cfg.direction != 45) {
+      // robot_env.py:46-54 `_get_direction` (disabled upstream at :29): unit vector at an arbitrary angle, theta rounded to 2 decimals
+      const double theta = std::round(cfg.direction * (3.14159265358979323846 / 180.0) * 100.0) / 100.0;
+      e.dir[0] = (float)std::cos(theta); e.dir[1] = (float)std::sin(theta);
+    }
     e.pos_tol = cfg.pos_tolerance; e.grasp_tol = cfg.grasp_tolerance; e.max_trans = cfg.max_translation; e.max_rot = cfg.max_rotation;
     // launch geometry: persistent blocks, as many as fit (one WS per warp in shared memory)
     s->smem = smem_bytes();

@@ -102,7 +102,7 @@ def _grs_config(config, auto_reset):
 class GripperSim(CompiledModel):
     """num_envs instances of the reference's RobotEnv (simulation/environment/robot_env.py) on one GPU.
 
-    config: Namespace as produced by the reference's BaseConfig (or make_config()); `direction` must be 0 or 45
+    config: Namespace as produced by the reference's BaseConfig (or make_config()); `direction` is 0 or 45 as in the reference, or any other angle in degrees
     (robot_env.py:30-33).  auto_reset=True gives SB3 VecEnv semantics (an environment is reset inside the step
     that ends its episode; the terminal observation is kept in `terminal_obs`).
     """

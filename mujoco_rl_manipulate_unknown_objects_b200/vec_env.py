@@ -72,6 +72,17 @@ def make_spaces(config):
     return obs, act
 
 
+def target_direction(direction):
+    """robot_env.py:30-33: 0 -> [1, 0], 45 -> [1, 1] (not normalised).  Any other angle in degrees gives the unit vector of the
+    reference's disabled `_get_direction` (robot_env.py:46-54; theta rounded to 2 decimals)."""
+    if direction == 0:
+        return np.array([1, 0])
+    if direction == 45:
+        return np.array([1, 1])
+    theta = np.round(np.deg2rad(direction), 2)
+    return np.array([np.cos(theta), np.sin(theta)])
+
+
 STATUS_NAMES = ("RUNNING", "FAIL", "TIME_LIMIT")  # RobotEnv.Status, robot_env.py:19-22
 
 
@@ -143,7 +154,7 @@ class BatchedRobotVecEnv(_VecEnvBase):
         if _VecEnvBase is not object:  # pragma: no cover
             super().__init__(num_envs, self.observation_space, self.action_space)
         self.num_envs = int(num_envs)
-        self.target_direction = np.array([1, 1]) if config.direction == 45 else np.array([1, 0])  # robot_env.py:30-33
+        self.target_direction = target_direction(config.direction)
         self._t_start = time.time()
         self._actions = None
         import torch

@@ -1224,6 +1224,11 @@ OEnv *orc_env_new(const OModel *m, const OEnvCfg *cfg, int body_ee, int body_obj
   e->finger2_body[0] = finger2[0]; e->finger2_body[1] = finger2[1];
   /* robot_env.py:30-33 — the direction vector is NOT normalised */
   e->target_dir[0] = 1; e->target_dir[1] = cfg->direction == 45 ? 1 : 0;
+  if (cfg->direction != 0 && cfg->direction != 45) {
+    /* robot_env.py:46-54 `_get_direction` (disabled upstream, :29): a unit vector at an arbitrary angle, theta rounded to 2 decimals */
+    double theta = round(cfg->direction * (M_PI / 180.0) * 100.0) / 100.0;
+    e->target_dir[0] = cos(theta); e->target_dir[1] = sin(theta);
+  }
   return e;
 }
 void orc_env_free(OEnv *e) { if (e) { orc_data_free(e->d); free(e); } }

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = [("sugar_cube", 0, {}, 3), ("sugar_cube", 45, {}, 4), ("sand_ball", 0, {}, 5), ("bread_crumb", 0, {}, 6), ("acorn", 0, {}, 7),
          ("sand_ball", 45, dict(include_roll=False), 8), ("sugar_cube", 0, dict(her_buffer=True, time_horizon=12), 9),
-         ("gripper_two_fingers", 0, {}, 10)]  # the primitive-box scene (mjc_PlaneBox + box support in MPR)
+         ("gripper_two_fingers", 0, {}, 10), ("sugar_cube", 120, {}, 11)]  # 120 degrees: the `_get_direction` unit vector (robot_env.py:46-54)  # the primitive-box scene (mjc_PlaneBox + box support in MPR)
 
 
 def make(scene, direction, kw, n, auto_reset=False):
@@ -74,7 +74,8 @@ def test_agent_step_at_matched_states(scene, direction, kw, seed):
     flipped = 0
     rew_err, qerrs = [], []
     L = engine.lib()
-    tdir = np.array([1.0, 1.0 if direction == 45 else 0.0])
+    from mujoco_rl_manipulate_unknown_objects_b200.vec_env import target_direction
+    tdir = np.ascontiguousarray(target_direction(direction), np.float64)
     zero2 = np.zeros(2)
     for i, r in enumerate(ref):
         # (1) the reward FUNCTION at matched inputs (reward.py:18-41 [+ robot_env.py:268-271]): always within 1e-4
