@@ -239,8 +239,9 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
     __syncthreads();
   }
   __shared__ unsigned long long t_sum[8], t_max[8], t_round[8];
-  __shared__ unsigned long long t_rounds;
-  if (TIMING) { if (threadIdx.x < 8) { t_sum[threadIdx.x] = 0; t_max[threadIdx.x] = 0; t_round[threadIdx.x] = 0; } if (threadIdx.x == 0) t_rounds = 0; __syncthreads(); }
+  __shared__ unsigned long long t_rounds, t_lone[8], t_lone_rounds;  // rounds in which exactly one warp of the block was active
+  int prev_active = 0;
+  if (TIMING) { if (threadIdx.x < 8) { t_sum[threadIdx.x] = 0; t_max[threadIdx.x] = 0; t_round[threadIdx.x] = 0; } if (threadIdx.x == 0) { t_rounds = 0; t_lone_rounds = 0; } if (threadIdx.x < 8) t_lone[threadIdx.x] = 0; __syncthreads(); }
   long long t0 = 0;
 #define LS_T0() if (TIMING) t0 = clock64();
 #define LS_T1(p) if (TIMING) { unsigned long long d_ = (unsigned long long)(clock64() - t0); if (lane == 0) { atomicAdd(&t_sum[p], d_); atomicMax(&t_round[p], d_); } }
@@ -272,8 +273,14 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
     }
     pos = pos || dyn;
     LS_T1(0);
-    if (!__syncthreads_or(pos)) break;
-    if (TIMING && threadIdx.x == 0) { for (int p = 0; p < 8; p++) { t_max[p] += t_round[p]; t_round[p] = 0; } t_rounds++; }
+    const int n_active = TIMING ? __syncthreads_count(pos) >> 5 : __syncthreads_or(pos);
+    if (!n_active) break;
+    if (TIMING && threadIdx.x == 0) {
+      for (int p = 0; p < 8; p++) { t_max[p] += t_round[p]; if (prev_active == 1) t_lone[p] += t_round[p]; t_round[p] = 0; }
+      t_rounds++;
+      if (prev_active == 1) t_lone_rounds++;
+    }
+    prev_active = n_active;
     // ---- the substep pipeline, stage by stage, whole block in step (dm_control legacy step: mj_step2 then mj_step1)
     LS_T0();
     if (dyn) smooth_forces(m, w, lane, true, t.f.xfrc_z);
@@ -322,7 +329,8 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
       s.debug[(size_t)blockIdx.x * 32 + threadIdx.x] = (float)t_sum[threadIdx.x] / (float)(blockDim.x >> 5);
       s.debug[(size_t)blockIdx.x * 32 + 8 + threadIdx.x] = (float)t_max[threadIdx.x];
     }
-    if (threadIdx.x == 0) s.debug[(size_t)blockIdx.x * 32 + 16] = (float)t_rounds;
+    if (threadIdx.x == 0) { s.debug[(size_t)blockIdx.x * 32 + 16] = (float)t_rounds; s.debug[(size_t)blockIdx.x * 32 + 17] = (float)t_lone_rounds; }
+    if (threadIdx.x < 8) s.debug[(size_t)blockIdx.x * 32 + 18 + threadIdx.x] = (float)t_lone[threadIdx.x];
   }
 #undef LS_T0
 #undef LS_T1

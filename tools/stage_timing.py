@@ -18,4 +18,7 @@ mean, mx = d[:, :7].sum(0), d[:, 8:15].sum(0)
 print("rounds per block: mean %.0f" % d[:, 16].mean())
 for n, a, b in zip(names, mean, mx):
     print("%-12s mean-warp %6.1f%%   block-max %6.1f%%   max/mean %.2f" % (n, 100 * a / mean.sum(), 100 * b / mx.sum(), b / max(a, 1)))
+lone = d[:, 18:25].sum(0); nl = d[:, 17].sum()
+print("rounds with a single active warp in the block: %d of %d; cycles per such round %.0f (= %.1f us at 1.965 GHz); stage shares: %s" % (
+    nl, d[:, 16].sum(), lone.sum() / max(nl, 1), lone.sum() / max(nl, 1) / 1965.0, ", ".join("%s %.0f%%" % (n, 100 * x / max(lone.sum(), 1)) for n, x in zip(names, lone))))
 print("total: sum of per-round maxima / sum of warp means = %.2f" % (mx.sum() / mean.sum()))
