@@ -135,7 +135,9 @@ GRS_API int32_t grs_render(grs_sim* sim, int32_t camera_id, int32_t width, int32
 
 /* number of kernels launched by this handle since creation (bench.py reports it as gpu_launches) */
 GRS_API uint64_t grs_launch_count(const grs_sim* sim);
-/* average device time (ms) of the fused step kernel over the launches since the last call (CUDA events on the stream) */
+/* average device time (ms) of the step kernel's PHYSICS phase over the launches since the last call.  Fused kernel (default):
+ * timed on the device (%globaltimer, first block start -> last block leaving the substep loop); otherwise CUDA events on the
+ * stream around the step kernel.  bench.py's roofline uses it. */
 GRS_API float grs_step_kernel_ms(grs_sim* sim, int32_t reset_counters);
 
 /* ---------------------------------------------------------------------------------------------------------------
