@@ -204,6 +204,11 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Programmatic dependent launch: this grid may have started while the previous layer was still running (its barrier
+  // initialisation and TMEM allocation above overlap that layer's tail).  Let the next layer do the same, then wait for the
+  // previous grid to complete and flush before the first read of its activations.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int nkb = a.K / BK;
@@ -625,9 +630,17 @@ extern "C" int32_t grp_get_params(const grp_policy* p, float* host, int64_t coun
 
 template <int MODE, int BN, int EPI>
 static void launch_layer(grp_policy* p, const LayerArgs& a, int n_total, cudaStream_t st) {
-  dim3 grid((a.M + BM - 1) / BM, n_total / BN);
-  k_layer<MODE, BN, EPI><<<grid, THREADS, layer_smem_bytes<MODE, BN>(), st>>>(a);
-  CU(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((a.M + BM - 1) / BM, n_total / BN);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = layer_smem_bytes<MODE, BN>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: see griddepcontrol in k_layer
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, k_layer<MODE, BN, EPI>, a));
   p->launches++;
 }
 
