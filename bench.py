@@ -38,8 +38,8 @@ BYTES_PER_TRANSITION = 21100  # state in/out + action + obs wr
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)  # >= 200 timed agent steps after >= 50 warm-up
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="acorn")
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")

@@ -406,12 +406,12 @@ __device__ __noinline__ int support_geom(const DevModel& m, const WS& w, const f
     float s = p.x * l[0] + p.y * l[1] + p.z * l[2];
     if (s > best) { best = s; bi = i; }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float ob = __shfl_xor_sync(FULL, best, o);
-    int oi = __shfl_xor_sync(FULL, bi, o);
-    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-  }
+  // warp arg-max, ties to the lowest vertex id: two integer warp reductions (redux.sync) on an order-preserving image of
+  // the float instead of five rounds of paired shuffles (the reduction, not the scan, dominates for hulls of <= 128 vertices)
+  unsigned key = __float_as_uint(best + 0.0f);  // + 0: -0 and +0 compare equal, as in the float comparison
+  key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
+  const unsigned kmax = __reduce_max_sync(FULL, key);
+  bi = (int)__reduce_min_sync(FULL, key == kmax ? (unsigned)bi : 0xffffffffu);
   float4 p = v[bi];
   float pv[3] = {p.x, p.y, p.z}, t[3];
   mulmat3vec(t, R, pv);

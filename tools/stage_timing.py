@@ -9,7 +9,10 @@ from mujoco_rl_manipulate_unknown_objects_b200 import GripperSim, make_config
 N = 4096
 sim = GripperSim(make_config(sim_env="/xmls/acorn_env.xml"), num_envs=N)
 gen = torch.Generator(device="cuda").manual_seed(0)
-for i in range(12):
+WARM = int(sys.argv[1]) if len(sys.argv) > 1 else 0  # agent steps before the measured ones (later states are contact-heavier)
+for i in range(WARM + 12):
+    if i == WARM:
+        torch.cuda.synchronize(); sim.debug.zero_()
     sim.step(torch.rand((N, 6), device="cuda", generator=gen) * 2 - 1)
 torch.cuda.synchronize()
 d = sim.debug.reshape(-1)[: 32 * 296].reshape(296, 32).cpu().numpy()
