@@ -391,6 +391,11 @@ __device__ __noinline__ void com_pos_crb(const DevModel& m, WS& w, int lane) {
 #define SUPV1(k) (w.sup[k] + 3)
 #define SUPV2(k) (w.sup[k] + 6)
 
+// order-preserving image of a float for integer warp reductions (see support_geom)
+__device__ __forceinline__ unsigned sortable_key(float x) {
+  const unsigned k = __float_as_uint(x + 0.0f);
+  return (k & 0x80000000u) ? ~k : (k | 0x80000000u);
+}
 // engine_collision_convex.c : mjccd_support for a hull — every lane scans a strided slice, arg-max by shuffles
 __device__ __noinline__ int support_geom(const DevModel& m, const WS& w, const float4* __restrict__ hv, int g, const float* dir, float* out, int lane) {
   const float* R = w.gmat[g];
@@ -403,13 +408,12 @@ __device__ __noinline__ int support_geom(const DevModel& m, const WS& w, const f
 #pragma unroll 2
   for (int i = lane; i < n; i += 32) {
     float4 p = v[i];  // generic load: the lock-step kernel stages the hulls in shared memory
-    float s = p.x * l[0] + p.y * l[1] + p.z * l[2];
+    float s = fmaf(p.z, l[2], fmaf(p.y, l[1], p.x * l[0]));  // explicit contraction: the same rounding in every copy of the scan
     if (s > best) { best = s; bi = i; }
   }
   // warp arg-max, ties to the lowest vertex id: two integer warp reductions (redux.sync) on an order-preserving image of
   // the float instead of five rounds of paired shuffles (the reduction, not the scan, dominates for hulls of <= 128 vertices)
-  unsigned key = __float_as_uint(best + 0.0f);  // + 0: -0 and +0 compare equal, as in the float comparison
-  key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
+  const unsigned key = sortable_key(best);  // (+ 0 inside: -0 and +0 compare equal, as in the float comparison)
   const unsigned kmax = __reduce_max_sync(FULL, key);
   bi = (int)__reduce_min_sync(FULL, key == kmax ? (unsigned)bi : 0xffffffffu);
   float4 p = v[bi];
@@ -418,13 +422,43 @@ __device__ __noinline__ int support_geom(const DevModel& m, const WS& w, const f
   out[0] = w.gpos[g][0] + t[0]; out[1] = w.gpos[g][1] + t[1]; out[2] = w.gpos[g][2] + t[2];
   return bi;
 }
-// libccd support.c : __ccdSupport on obj1 - obj2, each inflated by margin/2; result into portal slot `slot`
+// libccd support.c : __ccdSupport on obj1 - obj2, each inflated by margin/2; result into portal slot `slot`.
+// Both hull scans run in ONE loop (two independent compare chains per lane, two pairs of warp reductions back to back), so
+// a lone warp overlaps their latencies; vertex order, comparisons and tie rules are those of support_geom.
 __device__ __noinline__ void support_md(const DevModel& m, WS& w, const float4* hv, int g1, int g2, float margin, const float* dir, int slot, int lane) {
-  float n[3] = {dir[0], dir[1], dir[2]}, nd[3], v1[3], v2[3];
+  float n[3] = {dir[0], dir[1], dir[2]}, nd[3];
   normalize3(n);
   nd[0] = -n[0]; nd[1] = -n[1]; nd[2] = -n[2];
-  support_geom(m, w, hv, g1, n, v1, lane);
-  support_geom(m, w, hv, g2, nd, v2, lane);
+  const float *R1 = w.gmat[g1], *R2 = w.gmat[g2];
+  float l1[3], l2[3];
+  mulmat3Tvec(l1, R1, n);
+  mulmat3Tvec(l2, R2, nd);
+  const float4 *va = hv + m.geom_hvadr[g1], *vb = hv + m.geom_hvadr[g2];
+  const int na = m.geom_hvnum[g1], nb = m.geom_hvnum[g2], nmax = max(na, nb);
+  float besta = -3.0e38f, bestb = -3.0e38f;
+  int ia = 0, ib = 0;
+#pragma unroll 2
+  for (int i = lane; i < nmax; i += 32) {
+    if (i < na) {
+      const float4 p = va[i];
+      const float s = fmaf(p.z, l1[2], fmaf(p.y, l1[1], p.x * l1[0]));
+      if (s > besta) { besta = s; ia = i; }
+    }
+    if (i < nb) {
+      const float4 p = vb[i];
+      const float s = fmaf(p.z, l2[2], fmaf(p.y, l2[1], p.x * l2[0]));
+      if (s > bestb) { bestb = s; ib = i; }
+    }
+  }
+  const unsigned ka = sortable_key(besta), kb = sortable_key(bestb);
+  const unsigned kamax = __reduce_max_sync(FULL, ka), kbmax = __reduce_max_sync(FULL, kb);
+  ia = (int)__reduce_min_sync(FULL, ka == kamax ? (unsigned)ia : 0xffffffffu);
+  ib = (int)__reduce_min_sync(FULL, kb == kbmax ? (unsigned)ib : 0xffffffffu);
+  const float4 pa = va[ia], pb = vb[ib];
+  float pva[3] = {pa.x, pa.y, pa.z}, pvb[3] = {pb.x, pb.y, pb.z}, ta[3], tb[3], v1[3], v2[3];
+  mulmat3vec(ta, R1, pva);
+  mulmat3vec(tb, R2, pvb);
+  for (int k = 0; k < 3; k++) { v1[k] = w.gpos[g1][k] + ta[k]; v2[k] = w.gpos[g2][k] + tb[k]; }
   const float hm = 0.5f * margin;
   __syncwarp();
   if (lane < 3) {
