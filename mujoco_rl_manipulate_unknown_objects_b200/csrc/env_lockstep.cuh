@@ -206,7 +206,7 @@ __global__ void k_order_envs(SimBuffers s, const float* __restrict__ actions, in
 #ifndef LS_BARRIERS
 #define LS_BARRIERS 4
 #endif
-constexpr int LS_MAX_THREADS = 640;  // 20 warps: one block per SM (20 x 10.3 KB workspaces + the model in 227 KB of shared memory)
+constexpr int LS_MAX_THREADS = 512;  // 16 warps: leaves 128 registers per thread (2 blocks of 8 warps per SM in production)
 
 // TIMING = true: per-stage clock64 bookkeeping (sum over warps vs. per-round block maximum) into s.debug — a development
 // aid behind GRS_STEP_TIMING=1 that quantifies what the block barriers cost; the production instantiation carries none of it.

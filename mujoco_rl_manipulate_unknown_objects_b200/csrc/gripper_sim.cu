@@ -186,7 +186,7 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     if (per_sm < 1) throw std::runtime_error("step kernel does not fit on this device");
     int want = (num_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     s->grid = std::min(want, per_sm * nsm);
-    if (const char* e = getenv("GRS_STEP_WARPS")) s->ls_warps = std::max(0, std::min(20, atoi(e)));
+    if (const char* e = getenv("GRS_STEP_WARPS")) s->ls_warps = std::max(0, std::min(LS_MAX_THREADS / 32, atoi(e)));
     if (s->ls_warps > 0) {
       s->ls_smem = (sizeof(DevModel) + 15) / 16 * 16 + (size_t)s->ls_warps * sizeof(WS);
       {

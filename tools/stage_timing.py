@@ -19,6 +19,7 @@ d = sim.debug.reshape(-1)[: 32 * 296].reshape(296, 32).cpu().numpy()
 names = ["tick", "smooth", "constraint", "solve", "euler+kin", "crb", "collision"]
 mean, mx = d[:, :7].sum(0), d[:, 8:15].sum(0)
 print("rounds per block: mean %.0f" % d[:, 16].mean())
+print("kcycles per round: warp mean %s | block max %s" % (" ".join("%s %.1f" % (n, a / d[:, 16].sum() / 1e3) for n, a in zip(names, d[:, :7].sum(0))), " ".join("%.1f" % (b / d[:, 16].sum() / 1e3) for b in d[:, 8:15].sum(0))))
 for n, a, b in zip(names, mean, mx):
     print("%-12s mean-warp %6.1f%%   block-max %6.1f%%   max/mean %.2f" % (n, 100 * a / mean.sum(), 100 * b / mx.sum(), b / max(a, 1)))
 lone = d[:, 18:25].sum(0); nl = d[:, 17].sum()
