@@ -375,6 +375,7 @@ struct SimBuffers {
   const int* adj;
   const DevModel* model;
   int n;
+  int order_ncon;  // longest-first order: previous-step contact count from which an environment counts as contact-heavy
   int ls_mask;  // lock-step kernel: which stage boundaries carry a block barrier (bit 0 smooth | 1 constraint | 2 solve | 3 euler+kin | 4 crb)
 };
 constexpr int DEBUG_STRIDE = 2048;

@@ -102,7 +102,7 @@ static void harvest_events(grs_sim* s) {
   s->ev_n = 0;
 }
 
-static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, 8 * sizeof(int), st)); }
+static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, 48 * sizeof(int), st)); }
 
 extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs_config* cfg_in, int32_t device) {
   grs_sim* raw = nullptr;
@@ -147,12 +147,13 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     b.render_state = dalloc<float>(s.get(), N * RS_STRIDE);
     b.reset_record = dalloc<float>(s.get(), ST_STRIDE + IN_STRIDE + RS_STRIDE);
     b.debug = dalloc<float>(s.get(), N * DEBUG_STRIDE);
-    b.queue = dalloc<int>(s.get(), 8);
+    b.queue = dalloc<int>(s.get(), 48);
     b.done_list = dalloc<int>(s.get(), N);
     b.sm_phys = dalloc<int>(s.get(), 256);
     b.tstamp = dalloc<unsigned long long>(s.get(), 4);
     { const unsigned long long init[4] = {~0ull, 0, 0, 0}; CU(cudaMemcpy(b.tstamp, init, sizeof init, cudaMemcpyHostToDevice)); }
     b.ls_mask = 22;
+    b.order_ncon = getenv("GRS_ORDER_NCON") ? atoi(getenv("GRS_ORDER_NCON")) : 0;
     if (const char* e = getenv("GRS_LS_MASK")) b.ls_mask = atoi(e);
     b.order = dalloc<int>(s.get(), N);
     const size_t obs_bytes = (size_t)s->C * s->H * s->W;
@@ -282,7 +283,11 @@ extern "C" int32_t grs_step(grs_sim* s, const float* actions_dev, void* stream) 
     launch_queue_kernel_prep(s, st);
     if (s->ev_n == grs_sim::NEV) harvest_events(s);
     CU(cudaEventRecord(s->ev0[s->ev_n], st));
-    if (s->ls_warps > 0) { k_order_envs<<<(s->n + 255) / 256, 256, 0, st>>>(s->b, actions_dev, s->adim); s->launches++; }
+    if (s->ls_warps > 0) {
+      k_order_count<<<(s->n + 255) / 256, 256, 0, st>>>(s->b, actions_dev, s->adim);
+      k_order_envs<<<(s->n + 255) / 256, 256, 0, st>>>(s->b, actions_dev, s->adim);
+      s->launches += 2;
+    }
     const bool fused = s->ls_warps > 0 && s->fused_render;
     if (fused) k_env_step_ls<false, true><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim, s->scene, s->obs_args);
     else if (s->ls_warps > 0 && s->ls_timing) k_env_step_ls<true, false><<<s->ls_grid, s->ls_warps * 32, s->ls_smem, st>>>(s->b, s->ecfg, actions_dev, s->adim, s->scene, s->obs_args);
