@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
 #define LS_T1(p) if (TIMING) { unsigned long long d_ = (unsigned long long)(clock64() - t0); if (lane == 0) { atomicAdd(&t_sum[p], d_); atomicMax(&t_round[p], d_); } }
   EnvCtl t;
   t.stage = S_IDLE; t.env = -1;
-  bool exhausted = false;
+  bool exhausted = false, first = true;
   int iters = 0;
 #pragma unroll 1
   for (;;) {
@@ -277,7 +277,11 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
       if (!dyn) env_writeback(m, c, s, w, t, lane);
     }
     if (t.stage == S_IDLE && !exhausted) {
-      int slot = next_env(s.queue, lane);
+      // first environment of a warp: static slot, so that a block starts with consecutive queue entries (environments of the
+      // same class, see k_order_envs); later ones come from the shared counter, which starts behind the static slots
+      const int nstatic = gridDim.x * (blockDim.x >> 5);
+      int slot = first ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : nstatic + next_env(s.queue, lane);
+      first = false;
       if (slot < s.n) {
         const int env = __ldg(s.order + slot);
         t.env = env;
