@@ -167,3 +167,31 @@ def test_auto_reset_and_episode_bookkeeping():
     assert not torch.equal(sim.terminal_obs[0], sim.reset_obs)
     np.testing.assert_array_equal(sim.desired_goal.cpu().numpy()[0], np.float32([1, 0]))  # robot_env.py:72
     sim.close()
+
+
+def test_free_running_batch_statistics_match_the_oracle():
+    """No state injection at all: 128 environments x 60 agent steps of U(-1,1)^6 actions from reset, auto-reset on, on the GPU and
+    in the fp64 oracle (the bench's CPU arm).  Individual trajectories diverge once contacts start (chaotic map), the
+    aggregates must not: this pins the workload of bench.py's two arms to each other."""
+    import torch
+    from oracle import engine
+    n, steps = 128, 60
+    sim = make("sugar_cube", 0, {}, n, auto_reset=True)
+    om = oracle_model(sim)
+    rng = np.random.default_rng(7)
+    acts = rng.uniform(-1, 1, (n, steps, 6))
+    sub_ref, tr_ref, rsum_ref = engine.rollout_threads(om, acts, 8, direction=0)
+    sim.reset()
+    sub = rew = done = 0.0
+    for t in range(steps):
+        sim.step(torch.tensor(acts[:, t].astype(np.float32), device=sim.device))
+        info = sim.info.cpu().numpy()
+        sub += info[:, I["NSUB_A"]:I["NSUB_A"] + 3].sum()
+        rew += float(sim.reward.sum())
+        done += float(sim.done.sum())
+    print("\n[free-running batch] substeps gpu %d oracle %d (%.2f %%), reward sum gpu %.2f oracle %.2f, transitions %d / %d, episodes ended on gpu %d" % (
+        sub, sub_ref, 100 * (sub - sub_ref) / sub_ref, rew, rsum_ref, n * steps, tr_ref, done))
+    assert tr_ref == n * steps
+    assert abs(sub - sub_ref) / sub_ref < 0.03
+    assert abs(rew - rsum_ref) <= 0.15 * max(abs(rsum_ref), 1.0) + 1.0
+    sim.close()
