@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                         // STAGES x [128 rows x 128 B]
   uint8_t* sB = smem + STAGES * BM * 128;     // STAGES x [BN rows x 128 B]
+  __shared__ float sbias[BN];  // this CTA's slice of the bias (a parameter, not an activation: safe to read before griddepcontrol.wait)
+  for (int i = tid; i < BN; i += THREADS) sbias[i] = __ldg(a.bias + blockIdx.y * BN + i);
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) mbar_init(&bar_stage[s], 1);
     mbar_init(&bar_done, 1);
@@ -255,18 +257,29 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
     constexpr int PRE = 4;
     const unsigned char* obs = reinterpret_cast<const unsigned char*>(a.A);
     const int plane = a_kb_offset<CONV1>(a, 1);
+    // the reference's observation (64 x 64 planes, 4 image channels) on a full tile: every load is base + immediate
+    const bool fast = a.iw == 64 && a.ih == 64 && nkb == PRE && m0 + BM <= a.M;
 #pragma unroll 1
     for (int kb0 = 0; kb0 < nkb; kb0 += PRE) {
       uint2 raw[PRE][BM * 8 / THREADS];
+      if (fast) {
+        const unsigned char* p = obs + rbase[0];
 #pragma unroll
-      for (int i = 0; i < BM * 8 / THREADS; i++) {
-        const int base = rbase[i];
+        for (int i = 0; i < BM * 8 / THREADS; i++)
 #pragma unroll
-        for (int j = 0; j < PRE; j++) {
-          raw[j][i] = make_uint2(0, 0);
-          if (base >= 0 && kb0 + j < nkb) {
-            const unsigned char* src = obs + base + (kb0 + j) * plane;
-            raw[j][i] = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(src)), __ldg(reinterpret_cast<const uint32_t*>(src + 4)));
+          for (int j = 0; j < PRE; j++)
+            raw[j][i] = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(p + i * 64 + j * 4096)), __ldg(reinterpret_cast<const uint32_t*>(p + i * 64 + j * 4096 + 4)));
+      } else {
+#pragma unroll
+        for (int i = 0; i < BM * 8 / THREADS; i++) {
+          const int base = rbase[i];
+#pragma unroll
+          for (int j = 0; j < PRE; j++) {
+            raw[j][i] = make_uint2(0, 0);
+            if (base >= 0 && kb0 + j < nkb) {
+              const unsigned char* src = obs + base + (kb0 + j) * plane;
+              raw[j][i] = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(src)), __ldg(reinterpret_cast<const uint32_t*>(src + 4)));
+            }
           }
         }
       }
@@ -339,8 +352,8 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
     tmem_ld16(trow, v);
     if (row < a.M) {
       for (int k = 0; k < a.adim; k++) {
-        const float mu = v[k] + __ldg(a.bias + k);
-        float ls = v[8 + k] + __ldg(a.bias + 8 + k);
+        const float mu = v[k] + sbias[k];
+        float ls = v[8 + k] + sbias[8 + k];
         ls = fminf(fmaxf(ls, -20.0f), 2.0f);  // stable-baselines3 sac/policies.py LOG_STD_MIN / LOG_STD_MAX
         float pre = mu;
         if (a.noise) pre += __expf(ls) * a.noise[(size_t)row * a.adim + k];
@@ -358,8 +371,8 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
         uint32_t o[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-          const float x = fmaxf(v[2 * k] * a.scale + __ldg(a.bias + n0 + c0 + 2 * k), 0.0f);
-          const float y = fmaxf(v[2 * k + 1] * a.scale + __ldg(a.bias + n0 + c0 + 2 * k + 1), 0.0f);
+          const float x = fmaxf(v[2 * k] * a.scale + sbias[c0 + 2 * k], 0.0f);
+          const float y = fmaxf(v[2 * k + 1] * a.scale + sbias[c0 + 2 * k + 1], 0.0f);
           o[k] = pack_bf16(x, y);
         }
         uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)row * a.ldo + n0 + c0);
