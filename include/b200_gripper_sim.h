@@ -46,6 +46,12 @@ typedef struct grs_config {
   float grasp_tolerance;    /* base_config.py:31 (0.03) */
   float max_translation;    /* base_config.py:30 (0.05) */
   float max_rotation;       /* base_config.py:29 (0.15) */
+  /* Reset randomisation (the reference has none: RobotEnv.reset always starts from qpos0, robot_env.py:56-75).
+   * 0 / 0 (default) reproduces the reference.  Otherwise every reset moves the object by U(-xy, xy)^2 metres and turns it by
+   * U(-yaw, yaw) radians about the vertical, from a counter-based hash of (seed, environment, episode) — see INTEGRATION.md. */
+  float reset_noise_xy;
+  float reset_noise_yaw;
+  uint32_t seed;
 } grs_config;
 
 /* per-environment step record written by grs_step (robot_env.py:226-241 `info` + the return tuple) */

@@ -16,7 +16,7 @@ class GrsConfig(C.Structure):
                 ("full_observation", C.c_int32), ("im_reward", C.c_int32), ("her_buffer", C.c_int32),
                 ("direction", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("auto_reset", C.c_int32),
                 ("pos_tolerance", C.c_float), ("grasp_tolerance", C.c_float), ("max_translation", C.c_float),
-                ("max_rotation", C.c_float)]
+                ("max_rotation", C.c_float), ("reset_noise_xy", C.c_float), ("reset_noise_yaw", C.c_float), ("seed", C.c_uint32)]
 
 
 # record layouts (include/b200_gripper_sim.h)

@@ -8,7 +8,9 @@ ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 DEFAULTS = dict(sim_env="/xmls/acorn_env.xml", width_capture=64, height_capture=64, full_observation=True, camera_id=3,
                 show_obs=False, max_rotation=0.15, max_translation=0.05, grasp_tolerance=0.03, pos_tolerance=0.002,
                 include_roll=True, max_steps=400, im_reward=False, her_buffer=False, direction=0, time_horizon=400,
-                rendering_zoom_width=10, rendering_zoom_height=7.5)
+                rendering_zoom_width=10, rendering_zoom_height=7.5,
+                # not in the reference (its resets are deterministic): object pose jitter at reset, SURVEY.md §8f N4
+                reset_noise_xy=0.0, reset_noise_yaw=0.0, seed=0)
 
 
 def make_config(**overrides):

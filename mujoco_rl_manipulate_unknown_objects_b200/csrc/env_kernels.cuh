@@ -12,6 +12,8 @@ namespace grs {
 struct EnvCfg {
   int max_steps, time_horizon, include_roll, her_buffer, im_reward, auto_reset, full_observation, obs_cam;
   float dir[2], pos_tol, grasp_tol, max_trans, max_rot;
+  float reset_noise_xy, reset_noise_yaw;  // reset randomisation (0 = the reference's deterministic reset)
+  unsigned seed;
 };
 
 // indices of the packed records; mirrored by include/b200_gripper_sim.h (GRS_ST_*, GRS_INFO_*)
@@ -366,6 +368,8 @@ struct SimBuffers {
   int* queue;           // [0] work-queue counter, [1..2] bucket counters of the longest-first order, [3] finished environments,
                         // [4] observation tickets handed out, [5] blocks that left the fused kernel
   int* done_list;       // [N] environment ids in the order their agent steps finished (-1 = not yet); fused observation phase
+  int* episode_count;   // [N] resets taken so far (reset randomisation: the hash counter)
+  float* reset_obj;     // [N][12] pose (pos 3, mat 9) of the object geom at the start of the current episode (reset randomisation)
   int* sm_phys;         // [256] per SM: blocks of the fused kernel still in their physics phase (the observation phase yields to them)
   unsigned long long* tstamp;  // [0] first block start, [1] last physics-phase end (globaltimer ns), [2] sum of ([1]-[0]), [3] launches
   int* order;           // [N] environment ids, expected-long agent steps first (k_order_envs); identity for the other kernels
@@ -380,6 +384,42 @@ struct SimBuffers {
 };
 constexpr int DEBUG_STRIDE = 2048;
 constexpr int WARPS_PER_BLOCK = 4;
+
+
+// ---- reset randomisation (not in the reference).  u in [-1, 1) from a counter-based hash, so a reset is
+// a pure function of (seed, environment, episode index, k): any kernel, any order, reproducible; mirrored in tests/.
+__host__ __device__ inline float reset_uniform(unsigned seed, unsigned env, unsigned episode, unsigned k) {
+  unsigned h = seed * 0x9E3779B1u ^ env * 0x85EBCA77u ^ episode * 0xC2B2AE3Du ^ k * 0x27D4EB2Fu;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return (float)(h >> 8) * (2.0f / 16777216.0f) - 1.0f;
+}
+// `st` already holds the reset record.  Moves / turns the free object, records the pose of its geom for the observation of the
+// new episode and the achieved goal (object xy, robot_env.py:71).  One lane suffices (called by lane 0).
+__device__ inline void apply_reset_noise(const SimBuffers& s, const DevModel& m, const EnvCfg& c, int env, float* st) {
+  const unsigned ep = (unsigned)(s.episode_count[env] += 1);
+  const int qa = m.jnt_qposadr[m.body_jntadr[m.body_object]];  // free joint of the object: pos 3, quat 4
+  const float dx = c.reset_noise_xy * reset_uniform(c.seed, env, ep, 0), dy = c.reset_noise_xy * reset_uniform(c.seed, env, ep, 1);
+  const float yaw = c.reset_noise_yaw * reset_uniform(c.seed, env, ep, 2);
+  float p[3] = {st[ST_QPOS + qa] + dx, st[ST_QPOS + qa + 1] + dy, st[ST_QPOS + qa + 2]};
+  float q0[4] = {st[ST_QPOS + qa + 3], st[ST_QPOS + qa + 4], st[ST_QPOS + qa + 5], st[ST_QPOS + qa + 6]}, qz[4], q[4];
+  sincosf(0.5f * yaw, &qz[3], &qz[0]);
+  qz[1] = 0; qz[2] = 0;
+  quat_mul(q, qz, q0);  // world-frame yaw applied on the left
+  quat_normalize(q);
+  for (int k = 0; k < 3; k++) st[ST_QPOS + qa + k] = p[k];
+  for (int k = 0; k < 4; k++) st[ST_QPOS + qa + 3 + k] = q[k];
+  int g = 0;
+  for (int i = 0; i < m.ngeom; i++) if (m.geom_body[i] == m.body_object) { g = i; break; }
+  float R[9], Rg[9], t[3];
+  quat2mat(R, q);
+  quat2mat(Rg, m.geom_quat[g]);
+  mulmat3vec(t, R, m.geom_pos[g]);
+  float* o = s.reset_obj + (size_t)env * 12;
+  for (int k = 0; k < 3; k++) o[k] = p[k] + t[k];
+  for (int r = 0; r < 3; r++)
+    for (int cc = 0; cc < 3; cc++) o[3 + 3 * r + cc] = R[3 * r] * Rg[cc] + R[3 * r + 1] * Rg[3 + cc] + R[3 * r + 2] * Rg[6 + cc];
+  s.achieved[2 * env] = p[0]; s.achieved[2 * env + 1] = p[1];
+}
 
 extern __shared__ __align__(16) unsigned char grs_smem[];
 
@@ -427,9 +467,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) k_env_step(SimBuffers
     if (done && c.auto_reset) {
       // VecEnv semantics: the returned goals belong to the NEW episode (robot_env.py:71-72); the terminal ones stay in info
       for (int k = lane; k < ST_STRIDE; k += 32) st[k] = s.reset_record[k];
+      __syncwarp();
       if (lane == 0) {
         s.achieved[2 * env] = s.reset_record[ST_STRIDE + IN_ACHIEVED]; s.achieved[2 * env + 1] = s.reset_record[ST_STRIDE + IN_ACHIEVED + 1];
         s.desired[2 * env] = s.reset_record[ST_STRIDE + IN_DESIRED]; s.desired[2 * env + 1] = s.reset_record[ST_STRIDE + IN_DESIRED + 1];
+        if (c.reset_noise_xy != 0.f || c.reset_noise_yaw != 0.f) apply_reset_noise(s, m, c, env, st);
       }
     } else {
       store_state(w, f, st, lane);
@@ -476,7 +518,7 @@ __global__ void __launch_bounds__(32) k_make_reset_record(SimBuffers s, EnvCfg c
 }
 
 // RobotEnv.reset for the masked environments: copy the reset record
-__global__ void k_reset(SimBuffers s, const unsigned char* __restrict__ mask) {
+__global__ void k_reset(SimBuffers s, EnvCfg c, const unsigned char* __restrict__ mask) {
   const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (env >= s.n) return;
   if (mask && !mask[env]) return;
@@ -488,6 +530,8 @@ __global__ void k_reset(SimBuffers s, const unsigned char* __restrict__ mask) {
     s.achieved[2 * env] = s.reset_record[ST_STRIDE + IN_ACHIEVED]; s.achieved[2 * env + 1] = s.reset_record[ST_STRIDE + IN_ACHIEVED + 1];
     s.desired[2 * env] = s.reset_record[ST_STRIDE + IN_DESIRED]; s.desired[2 * env + 1] = s.reset_record[ST_STRIDE + IN_DESIRED + 1];
   }
+  __syncwarp();
+  if (lane == 0 && (c.reset_noise_xy != 0.f || c.reset_noise_yaw != 0.f)) apply_reset_noise(s, *s.model, c, env, s.state + (size_t)env * ST_STRIDE);
 }
 
 // n x physics.step() with the controls held in the state (parity tests; robot_env.py:100)

@@ -174,9 +174,11 @@ __device__ __noinline__ void env_writeback(const DevModel& m, const EnvCfg& c, c
   }
   if (done && c.auto_reset) {
     for (int k = lane; k < ST_STRIDE; k += 32) st[k] = s.reset_record[k];
+    __syncwarp();
     if (lane == 0) {
       s.achieved[2 * env] = s.reset_record[ST_STRIDE + IN_ACHIEVED]; s.achieved[2 * env + 1] = s.reset_record[ST_STRIDE + IN_ACHIEVED + 1];
       s.desired[2 * env] = s.reset_record[ST_STRIDE + IN_DESIRED]; s.desired[2 * env + 1] = s.reset_record[ST_STRIDE + IN_DESIRED + 1];
+      if (c.reset_noise_xy != 0.f || c.reset_noise_yaw != 0.f) apply_reset_noise(s, m, c, env, st);
     }
   } else {
     store_state(w, t.f, st, lane);

@@ -83,6 +83,7 @@ extern "C" void grs_default_config(grs_config* c) {
   c->max_steps = 400; c->time_horizon = 400; c->include_roll = 1; c->full_observation = 1; c->im_reward = 0; c->her_buffer = 0;
   c->direction = 0; c->width = 64; c->height = 64; c->auto_reset = 1;
   c->pos_tolerance = 0.002f; c->grasp_tolerance = 0.03f; c->max_translation = 0.05f; c->max_rotation = 0.15f;
+  c->reset_noise_xy = 0.0f; c->reset_noise_yaw = 0.0f; c->seed = 0;
 }
 
 extern "C" grs_sim* grs_compile_only(const char* xml_path) {
@@ -150,6 +151,8 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     b.queue = dalloc<int>(s.get(), 48);
     b.done_list = dalloc<int>(s.get(), N);
     b.sm_phys = dalloc<int>(s.get(), 256);
+    b.episode_count = dalloc<int>(s.get(), N);
+    b.reset_obj = dalloc<float>(s.get(), N * 12);
     b.tstamp = dalloc<unsigned long long>(s.get(), 4);
     { const unsigned long long init[4] = {~0ull, 0, 0, 0}; CU(cudaMemcpy(b.tstamp, init, sizeof init, cudaMemcpyHostToDevice)); }
     b.ls_mask = 22;
@@ -173,6 +176,8 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
       const double theta = std::round(cfg.direction * (3.14159265358979323846 / 180.0) * 100.0) / 100.0;
       e.dir[0] = (float)std::cos(theta); e.dir[1] = (float)std::sin(theta);
     }
+    if (!(cfg.reset_noise_xy >= 0.f) || !(cfg.reset_noise_yaw >= 0.f)) throw std::runtime_error("reset_noise_xy / reset_noise_yaw must be >= 0");
+    e.reset_noise_xy = cfg.reset_noise_xy; e.reset_noise_yaw = cfg.reset_noise_yaw; e.seed = cfg.seed;
     e.pos_tol = cfg.pos_tolerance; e.grasp_tol = cfg.grasp_tolerance; e.max_trans = cfg.max_translation; e.max_rot = cfg.max_rotation;
     // launch geometry: persistent blocks, as many as fit (one WS per warp in shared memory)
     s->smem = smem_bytes();
@@ -225,6 +230,17 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     }
     s->launches++;
     CU(cudaStreamSynchronize(s->stream));
+    {
+      // reset randomisation: the new episode's observation is rendered per environment (object geom at its own pose)
+      float rinfo[IN_STRIDE];
+      CU(cudaMemcpy(rinfo, s->b.reset_record + ST_STRIDE, sizeof rinfo, cudaMemcpyDeviceToHost));
+      oa.reset_noise = (e.reset_noise_xy != 0.f || e.reset_noise_yaw != 0.f) ? 1 : 0;
+      oa.obj_geom = 0;
+      for (int g = 0; g < s->hm.ngeom; g++) if (s->hm.geom_bodyid[g] == s->hm.body_object) { oa.obj_geom = g; break; }
+      oa.reset_rs = s->b.reset_record + ST_STRIDE + IN_STRIDE;
+      oa.reset_obj = s->b.reset_obj;
+      oa.reset_pad0 = (unsigned char)rinfo[IN_GRASP]; oa.reset_pad1 = (unsigned char)rinfo[IN_PHEROMONE];
+    }
     if (grs_reset(s.get(), nullptr, nullptr) != 0) throw std::runtime_error(g_err);
     CU(cudaStreamSynchronize(s->stream));
     return s.release();
@@ -266,9 +282,10 @@ extern "C" int32_t grs_reset(grs_sim* s, const uint8_t* mask_dev, void* stream) 
     CU(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
     const int wpb = 8;
-    k_reset<<<(s->n + wpb - 1) / wpb, wpb * 32, 0, st>>>(s->b, mask_dev);
+    k_reset<<<(s->n + wpb - 1) / wpb, wpb * 32, 0, st>>>(s->b, s->ecfg, mask_dev);
     CU(cudaGetLastError());
-    launch_copy_reset_obs(s->d_obs, s->d_reset_obs, s->d_hist, s->d_hist + (size_t)s->n * 512, mask_dev, s->n, s->C * s->H * s->W, st);
+    if (s->obs_args.reset_noise) launch_render_reset(s->scene, s->obs_args, mask_dev, s->n, st);
+    else launch_copy_reset_obs(s->d_obs, s->d_reset_obs, s->d_hist, s->d_hist + (size_t)s->n * 512, mask_dev, s->n, s->C * s->H * s->W, st);
     s->launches += 2;
     return 0;
   } catch (const std::exception& e) { return fail(e.what()); }

@@ -388,6 +388,12 @@ struct ObsArgs {
   int C, H, W;
   float fovy;
   int auto_reset, im_reward;
+  // reset randomisation: the observation of a new episode is rendered (reset record's scene with the object geom at its
+  // per-environment pose) instead of copied from the constant reset image
+  int reset_noise, obj_geom;
+  const float* reset_rs;   // [RS_STRIDE] render state of the reset record
+  const float* reset_obj;  // [n][12] object geom pose of each environment's current episode
+  unsigned char reset_pad0, reset_pad1;  // pad-channel scalars of a freshly reset environment
 };
 
 // Observation of ONE environment by one block of RTHREADS threads (the observation is a single tile, W,H <= 64):
@@ -396,14 +402,11 @@ struct ObsArgs {
 //   rs       : this env's render state (geom poses + camera), any address space
 //   pad0/1   : grasp / pheromone scalars of the pad channel;  is_done : done flag of the step just taken
 //   reward   : per-env reward array (the intrinsic term is added in place), or NULL
-__device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsArgs& o, const float* rs, int env, unsigned char pad0, unsigned char pad1,
-                                               bool is_done, float* reward, TileShared& sh, unsigned* rgb8) {
-  const int tid = threadIdx.x, C = o.C, H = o.H, W = o.W, auto_reset = o.auto_reset, im_reward = o.im_reward;
-  unsigned char* obs = o.obs;
-  unsigned char* terminal_obs = o.terminal_obs;
-  const unsigned char* reset_obs = o.reset_obs;
-  float* hist_prev = o.hist_prev;
-  float* hist_reset = o.hist_reset;
+// rasterise + shade the scene `rs`, transform_depth, pack uint8 CHW with the two scalar channels into `dst`, histograms of the
+// grey image and of the depth channel into sh.hist
+__device__ __forceinline__ void render_and_pack(const RenderScene& sc, const ObsArgs& o, const float* rs, unsigned char* dst, unsigned char pad0, unsigned char pad1,
+                                                TileShared& sh, unsigned* rgb8) {
+  const int tid = threadIdx.x, C = o.C, H = o.H, W = o.W;
   render_tile(sc, rs, sh, rgb8, W, H, 0, 0, W, H, o.fovy);
   const int npix = W * H;
   // transform_depth (utils.py:11-19): d -= min(d); d /= 2*mean(d[d <= 1]); 255*clip(d, 0, 1)
@@ -420,7 +423,6 @@ __device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsA
   const float denom = 2.0f * (sm / cnt);  // cnt >= 1: the minimum pixel itself
   for (int i = tid; i < 512; i += RTHREADS) (&sh.hist[0][0])[i] = 0;
   __syncthreads();
-  unsigned char* dst = (is_done && auto_reset) ? terminal_obs + (size_t)env * C * npix : obs + (size_t)env * C * npix;
   for (int i = tid; i < npix; i += RTHREADS) {
     int y = i / W, x = i - y * W;
     unsigned c = rgb8[y * TILE + x];
@@ -438,6 +440,28 @@ __device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsA
     atomicAdd(&sh.hist[1][d8], 1u);
   }
   __syncthreads();
+}
+
+// scene of a freshly reset environment with the object geom at this environment's pose -> rs2 (shared memory, RS_STRIDE floats)
+__device__ __forceinline__ void build_reset_scene(const ObsArgs& o, int env, float* rs2) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid < RS_STRIDE) {
+    const int g = tid / 12;
+    rs2[tid] = (g == o.obj_geom && tid < 84) ? __ldcg(o.reset_obj + (size_t)env * 12 + (tid - 12 * g)) : o.reset_rs[tid];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsArgs& o, const float* rs, int env, unsigned char pad0, unsigned char pad1,
+                                               bool is_done, float* reward, TileShared& sh, unsigned* rgb8, float* rs2) {
+  const int tid = threadIdx.x, C = o.C, auto_reset = o.auto_reset, im_reward = o.im_reward, npix = o.W * o.H;
+  unsigned char* obs = o.obs;
+  const unsigned char* reset_obs = o.reset_obs;
+  float* hist_prev = o.hist_prev;
+  float* hist_reset = o.hist_reset;
+  unsigned char* dst = (is_done && auto_reset) ? o.terminal_obs + (size_t)env * C * npix : obs + (size_t)env * C * npix;
+  render_and_pack(sc, o, rs, dst, pad0, pad1, sh, rgb8);
   // intrinsic reward (reward.py:57-77): KL(old || new) of the grey (and depth) histograms, float32 pdfs
   float* hp = hist_prev ? hist_prev + (size_t)env * 512 : nullptr;
   if (im_reward && reward && hp) {
@@ -455,11 +479,17 @@ __device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsA
   __syncthreads();
   if (is_done && auto_reset) {
     // SB3 VecEnv: the returned observation is the first one of the next episode; the terminal one went to terminal_obs
-    const uint4* src = reinterpret_cast<const uint4*>(reset_obs);
-    uint4* o4 = reinterpret_cast<uint4*>(obs + (size_t)env * C * npix);
-    if ((C * npix) % 16 == 0) { for (int i = tid; i < C * npix / 16; i += RTHREADS) o4[i] = src[i]; }
-    else { for (int i = tid; i < C * npix; i += RTHREADS) obs[(size_t)env * C * npix + i] = reset_obs[i]; }
-    if (hp) for (int i = tid; i < 512; i += RTHREADS) hp[i] = hist_reset[i];
+    if (o.reset_noise) {
+      build_reset_scene(o, env, rs2);
+      render_and_pack(sc, o, rs2, obs + (size_t)env * C * npix, o.reset_pad0, o.reset_pad1, sh, rgb8);
+      if (hp) for (int i = tid; i < 512; i += RTHREADS) hp[i] = (float)(&sh.hist[0][0])[i];
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(reset_obs);
+      uint4* o4 = reinterpret_cast<uint4*>(obs + (size_t)env * C * npix);
+      if ((C * npix) % 16 == 0) { for (int i = tid; i < C * npix / 16; i += RTHREADS) o4[i] = src[i]; }
+      else { for (int i = tid; i < C * npix; i += RTHREADS) obs[(size_t)env * C * npix + i] = reset_obs[i]; }
+      if (hp) for (int i = tid; i < 512; i += RTHREADS) hp[i] = hist_reset[i];
+    }
   } else {
     float* ho = hp ? hp : hist_reset;
     if (ho) for (int i = tid; i < 512; i += RTHREADS) ho[i] = (float)(&sh.hist[0][0])[i];
@@ -473,9 +503,23 @@ __global__ void __launch_bounds__(RTHREADS) k_render_obs(RenderScene sc, ObsArgs
   extern __shared__ __align__(16) unsigned char rsm[];
   TileShared& sh = *reinterpret_cast<TileShared*>(rsm);
   unsigned* rgb8 = reinterpret_cast<unsigned*>(rsm + sizeof(TileShared));
+  float* rs2 = reinterpret_cast<float*>(rsm + sizeof(TileShared) + TILE * TILE * sizeof(unsigned));
   const int env = blockIdx.x;
   const float* inf = info + (size_t)env * info_stride;
-  render_obs_env(sc, o, render_state + (size_t)env * RS_STRIDE, env, (unsigned char)inf[IN_GRASP], (unsigned char)inf[IN_PHEROMONE], done ? done[env] != 0 : false, reward, sh, rgb8);
+  render_obs_env(sc, o, render_state + (size_t)env * RS_STRIDE, env, (unsigned char)inf[IN_GRASP], (unsigned char)inf[IN_PHEROMONE], done ? done[env] != 0 : false, reward, sh, rgb8, rs2);
+}
+
+// Explicit reset with reset randomisation: observation (and histograms) of the masked environments' new episodes
+__global__ void __launch_bounds__(RTHREADS) k_render_reset(RenderScene sc, ObsArgs o, const unsigned char* __restrict__ mask) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  TileShared& sh = *reinterpret_cast<TileShared*>(rsm);
+  unsigned* rgb8 = reinterpret_cast<unsigned*>(rsm + sizeof(TileShared));
+  float* rs2 = reinterpret_cast<float*>(rsm + sizeof(TileShared) + TILE * TILE * sizeof(unsigned));
+  const int env = blockIdx.x, npix = o.W * o.H;
+  if (mask && !mask[env]) return;
+  build_reset_scene(o, env, rs2);
+  render_and_pack(sc, o, rs2, o.obs + (size_t)env * o.C * npix, o.reset_pad0, o.reset_pad1, sh, rgb8);
+  if (o.hist_prev) for (int i = threadIdx.x; i < 512; i += RTHREADS) o.hist_prev[(size_t)env * 512 + i] = (float)(&sh.hist[0][0])[i];
 }
 
 inline size_t render_smem_bytes() { return sizeof(TileShared) + TILE * TILE * sizeof(unsigned); }
@@ -516,7 +560,7 @@ __device__ __forceinline__ void render_phase(const RenderScene& sc, const ObsArg
     const unsigned char pad0 = (unsigned char)__ldcg(inf + IN_GRASP), pad1 = (unsigned char)__ldcg(inf + IN_PHEROMONE);
     const bool is_done = __ldcg(s.done + env) != 0;
     __syncthreads();
-    render_obs_env(sc, o, rs, env, pad0, pad1, is_done, s.reward, sh, rgb8);
+    render_obs_env(sc, o, rs, env, pad0, pad1, is_done, s.reward, sh, rgb8, rs);  // rs is dead once the terminal image is packed
   }
 }
 
@@ -526,11 +570,17 @@ inline void launch_render_obs(const RenderScene& sc, const ObsArgs& o, const flo
   if (o.W > TILE || o.H > TILE) throw std::runtime_error("observation size above 64x64 is not supported by the fused observation kernel");
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(k_render_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_smem_bytes()) != cudaSuccess) throw std::runtime_error("cudaFuncSetAttribute(k_render_obs)");
+    if (cudaFuncSetAttribute(k_render_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_phase_smem_bytes()) != cudaSuccess) throw std::runtime_error("cudaFuncSetAttribute(k_render_obs)");
+    if (cudaFuncSetAttribute(k_render_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_phase_smem_bytes()) != cudaSuccess) throw std::runtime_error("cudaFuncSetAttribute(k_render_reset)");
     attr = true;
   }
-  k_render_obs<<<n, RTHREADS, render_smem_bytes(), st>>>(sc, o, render_state, info, IN_STRIDE, done, reward);
+  k_render_obs<<<n, RTHREADS, render_phase_smem_bytes(), st>>>(sc, o, render_state, info, IN_STRIDE, done, reward);
   if (cudaGetLastError() != cudaSuccess) throw std::runtime_error("k_render_obs launch failed");
+}
+
+inline void launch_render_reset(const RenderScene& sc, const ObsArgs& o, const unsigned char* mask, int n, cudaStream_t st) {
+  k_render_reset<<<n, RTHREADS, render_phase_smem_bytes(), st>>>(sc, o, mask);
+  if (cudaGetLastError() != cudaSuccess) throw std::runtime_error("k_render_reset launch failed");
 }
 
 // reset path: copy the constant reset image (and its histograms) into the masked environments

@@ -96,6 +96,8 @@ def _grs_config(config, auto_reset):
     c.auto_reset = int(bool(auto_reset))
     c.pos_tolerance, c.grasp_tolerance = float(config.pos_tolerance), float(config.grasp_tolerance)
     c.max_translation, c.max_rotation = float(config.max_translation), float(config.max_rotation)
+    c.reset_noise_xy, c.reset_noise_yaw = float(getattr(config, "reset_noise_xy", 0.0)), float(getattr(config, "reset_noise_yaw", 0.0))
+    c.seed = int(getattr(config, "seed", 0)) & 0xFFFFFFFF
     return c
 
 
