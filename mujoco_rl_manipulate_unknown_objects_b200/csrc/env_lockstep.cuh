@@ -196,16 +196,18 @@ __device__ __noinline__ void env_writeback(const DevModel& m, const EnvCfg& c, c
 // start in the first wave; short ones fill the slots that free up.  Order within a bucket is irrelevant to the results.
 // A second key groups environments of similar cost per substep: a lock-step round lasts as long as its slowest warp in each
 // stage, and the expensive stage (narrowphase: full MPR runs) is expensive exactly for environments whose gripper touches
-// something.  The contact count of the previous agent step is the predictor.  Four classes, queued in the order
-// (long, contact) (long, free) (short, contact) (short, free); k_order_count sizes them, k_order_envs places.
-constexpr int ORDER_BUCKETS = 8;  // contact-count buckets per chain-length class; counters live in SimBuffers::queue[16..47]
+// something.  The contact count of the previous agent step is the predictor.  Classes are queued chain-length class first
+// (close the gripper | open it | arm only), most contacts first inside each; k_order_count sizes them, k_order_envs places.
+constexpr int ORDER_BUCKETS = 8;  // contact-count buckets per chain-length class; 3 x 8 classes; counters live in SimBuffers::queue[16..39] (sizes) and [40..63] (cursors)
 __device__ __forceinline__ int order_class(const SimBuffers& s, const float* __restrict__ actions, int adim, int env) {
   const float oc = actions[(size_t)env * adim + adim - 1];
   const bool open = s.state[(size_t)env * ST_STRIDE + ST_GRIPPER_OPEN] != 0.0f;
-  const bool is_long = (oc > 0.f && !open) || (oc < 0.f && open);
+  // chain-length class: closing the gripper (~175 extra substeps) | opening it (~75) | arm only
+  const int len = (oc < 0.f && open) ? 0 : (oc > 0.f && !open) ? 1 : 2;
   const int ncon = (int)s.info[(size_t)env * IN_STRIDE + IN_NCON_MAX];
-  if (s.order_ncon > 0) return (is_long ? 0 : ORDER_BUCKETS) + (ncon >= s.order_ncon ? 0 : 1);  // two-level variant (sweeps)
-  return (is_long ? 0 : ORDER_BUCKETS) + (ORDER_BUCKETS - 1 - min(max(ncon, 0), ORDER_BUCKETS - 1));  // most contacts first
+  if (s.order_ncon > 0) return (len == 2 ? ORDER_BUCKETS : 0) + (ncon >= s.order_ncon ? 0 : 1);  // two-level variant (sweeps)
+  if (s.order_ncon < 0) return (len == 2 ? ORDER_BUCKETS : 0) + (ORDER_BUCKETS - 1 - min(max(ncon, 0), ORDER_BUCKETS - 1));  // long | short only
+  return len * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - min(max(ncon, 0), ORDER_BUCKETS - 1));  // most contacts first
 }
 __global__ void k_order_count(SimBuffers s, const float* __restrict__ actions, int adim) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,7 +220,7 @@ __global__ void k_order_envs(SimBuffers s, const float* __restrict__ actions, in
   const int c = order_class(s, actions, adim, env);
   int base = 0;
   for (int k = 0; k < c; k++) base += s.queue[16 + k];
-  s.order[base + atomicAdd(s.queue + 32 + c, 1)] = env;
+  s.order[base + atomicAdd(s.queue + 40 + c, 1)] = env;
   s.done_list[env] = -1;
 }
 

@@ -103,7 +103,7 @@ static void harvest_events(grs_sim* s) {
   s->ev_n = 0;
 }
 
-static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, 48 * sizeof(int), st)); }
+static void launch_queue_kernel_prep(grs_sim* s, cudaStream_t st) { CU(cudaMemsetAsync(s->b.queue, 0, 64 * sizeof(int), st)); }
 
 extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs_config* cfg_in, int32_t device) {
   grs_sim* raw = nullptr;
@@ -148,7 +148,7 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     b.render_state = dalloc<float>(s.get(), N * RS_STRIDE);
     b.reset_record = dalloc<float>(s.get(), ST_STRIDE + IN_STRIDE + RS_STRIDE);
     b.debug = dalloc<float>(s.get(), N * DEBUG_STRIDE);
-    b.queue = dalloc<int>(s.get(), 48);
+    b.queue = dalloc<int>(s.get(), 64);
     b.done_list = dalloc<int>(s.get(), N);
     b.sm_phys = dalloc<int>(s.get(), 256);
     b.episode_count = dalloc<int>(s.get(), N);
