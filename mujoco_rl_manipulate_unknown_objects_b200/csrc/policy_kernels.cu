@@ -399,22 +399,24 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
 // ------------------------------------------------------------------------------------------------ conv1, one image per CTA
 // The reference's observation (64 x 64, 4 image planes = one contiguous 16 KB block of the [n][C][64][64] uint8 tensor) is
 // brought into shared memory by ONE bulk asynchronous copy (cp.async.bulk, the TMA engine's 1-D path) that completes on an
-// mbarrier.  The 225 output pixels of the image are two 128-row MMA tiles; for each tile every thread builds the whole K = 256
-// row of its output pixel from shared memory (32 chunks of 8 pixels: shared loads at compile-time offsets, byte permutes, HSUB2;
-// no global address arithmetic, no global latency), then 16 MMAs (K = 16 each) run over the four staged k-blocks at once.
+// mbarrier.  The 225 output pixels of the image are two 128-row MMA tiles (TMEM columns 0-31 and 32-63); thread t of the 256
+// builds the K row of output pixel t from shared memory, one K half (two input channels) at a time (16 chunks of 8 pixels:
+// shared loads at compile-time offsets, byte permutes, HSUB2; no global address arithmetic, no global latency); the MMAs of a
+// half run while the next half is being converted.
+constexpr int C1_THREADS = 256;                // thread t: output pixel t (tile 0: pixels 0..127, tile 1: 128..224 + padding)
 constexpr int C1_IMG = 4 * 64 * 64;            // staged uint8 planes
-constexpr int C1_A = 4 * BM * 128;             // four k-blocks of A, K-major SWIZZLE_128B
+constexpr int C1_A = 2 * 2 * BM * 128;         // two tiles x two k-blocks of A (one K half at a time), K-major SWIZZLE_128B
 constexpr int C1_W = 4 * 32 * 128;             // four k-blocks of W (32 output channels)
 constexpr size_t C1_SMEM = C1_IMG + C1_A + C1_W + 1024;
 
-__global__ void __launch_bounds__(THREADS) k_conv1_image(const LayerArgs a) {
+__global__ void __launch_bounds__(C1_THREADS) k_conv1_image(const LayerArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_img, bar_mma;
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[32];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                  // 4 x [128 rows x 128 B]
+  uint8_t* sA = smem;                  // [tile 2][k-block of the current half 2][128 rows x 128 B]
   uint8_t* sB = smem + C1_A;           // 4 x [32 rows x 128 B]
   uint8_t* img = smem + C1_A + C1_W;   // [4][64][64] uint8
   if (tid < 32) sbias[tid] = __ldg(a.bias + tid);
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(THREADS) k_conv1_image(const LayerArgs a) {
     fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(&tmem_base_s, 32);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);  // columns 0..31: tile 0, 32..63: tile 1
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -440,8 +442,8 @@ __global__ void __launch_bounds__(THREADS) k_conv1_image(const LayerArgs a) {
                  ::"r"(smem_u32(img)), "l"(src), "r"(C1_IMG), "r"(smem_u32(&bar_img)) : "memory");
   }
 #pragma unroll
-  for (int i = 0; i < 4 * 32 * 8 / THREADS; i++) {
-    const int c = i * THREADS + tid, kb = c >> 8, row = (c >> 3) & 31, ch = c & 7;
+  for (int i = 0; i < 4 * 32 * 8 / C1_THREADS; i++) {
+    const int c = i * C1_THREADS + tid, kb = c >> 8, row = (c >> 3) & 31, ch = c & 7;
     cp_async16(smem_u32(sB + kb * 32 * 128 + row * 128 + ((ch ^ (row & 7)) << 4)), a.W + (size_t)row * a.K + kb * BK + ch * 8, true);
   }
   cp_async_commit();
@@ -449,21 +451,26 @@ __global__ void __launch_bounds__(THREADS) k_conv1_image(const LayerArgs a) {
   cp_async_wait<0>();
   constexpr uint32_t idesc = instr_desc_f16(BM, 32, false);
   const int per = 15 * 15;
+  const int tile = tid >> 7, row = tid & 127, p = tid;  // output pixel of this thread
+  const bool valid = p < per;
+  const int oy = valid ? p / 15 : 0, ox = valid ? p - oy * 15 : 0;
+  const uint8_t* src = img + (4 * oy) * 64 + 4 * ox;
+  uint8_t* dst = sA + tile * 2 * BM * 128 + row * 128;
+  const int sw = row & 7;
 #pragma unroll 1
-  for (int tile = 0; tile < 2; tile++) {
-    const int p = tile * BM + tid;  // output pixel of this thread
-    const bool valid = p < per;
-    const int oy = valid ? p / 15 : 0, ox = valid ? p - oy * 15 : 0;
-    const uint8_t* src = img + (4 * oy) * 64 + 4 * ox;
-    const int sw = tid & 7;
-    uint8_t* dst = sA + tid * 128;
+  for (int half = 0; half < 2; half++) {
+    if (half) {  // the MMAs of the first K half read the A buffers that are about to be overwritten
+      mbar_wait(&bar_mma, 0);
+      tc_fence_after();
+    }
 #pragma unroll
-    for (int kb = 0; kb < 4; kb++) {
+    for (int kk = 0; kk < 2; kk++) {
+      const int kb = half * 2 + kk;
 #pragma unroll
       for (int ky = 0; ky < 8; ky++) {
         uint2 raw = make_uint2(0, 0);
         if (valid) raw = make_uint2(*reinterpret_cast<const uint32_t*>(src + kb * 4096 + ky * 64), *reinterpret_cast<const uint32_t*>(src + kb * 4096 + ky * 64 + 4));
-        *reinterpret_cast<uint4*>(dst + kb * BM * 128 + ((ky ^ sw) << 4)) = u8x8_to_f16x8(raw);
+        *reinterpret_cast<uint4*>(dst + kk * BM * 128 + ((ky ^ sw) << 4)) = u8x8_to_f16x8(raw);
       }
     }
     fence_async_smem();
@@ -471,36 +478,37 @@ __global__ void __launch_bounds__(THREADS) k_conv1_image(const LayerArgs a) {
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int kb = 0; kb < 4; kb++) {
-        const uint32_t aaddr = smem_u32(sA + kb * BM * 128), baddr = smem_u32(sB + kb * 32 * 128);
+      for (int t = 0; t < 2; t++)
 #pragma unroll
-        for (int k = 0; k < BK / 16; k++) umma_bf16(tmem, smem_desc_sw128(aaddr + k * 32), smem_desc_sw128(baddr + k * 32), idesc, (kb | k) != 0);
-      }
+        for (int kk = 0; kk < 2; kk++) {
+          const uint32_t aaddr = smem_u32(sA + (t * 2 + kk) * BM * 128), baddr = smem_u32(sB + (half * 2 + kk) * 32 * 128);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) umma_bf16(tmem + t * 32, smem_desc_sw128(aaddr + k * 32), smem_desc_sw128(baddr + k * 32), idesc, (half | kk | k) != 0);
+        }
       umma_commit(&bar_mma);
     }
-    mbar_wait(&bar_mma, tile & 1);
-    tc_fence_after();
-    // ---- epilogue: thread t of warp w owns accumulator row 32*w + t = output pixel p
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-#pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 16) {
-      float v[16];
-      tmem_ld16(trow + c0, v);
-      if (valid) {
-        uint32_t o[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          o[k] = pack_bf16(fmaxf(v[2 * k] * a.scale + sbias[c0 + 2 * k], 0.0f), fmaxf(v[2 * k + 1] * a.scale + sbias[c0 + 2 * k + 1], 0.0f));
-        uint4* out = reinterpret_cast<uint4*>(a.out + ((size_t)n * per + p) * 32 + c0);
-        out[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        out[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      }
-    }
-    tc_fence_before();
-    __syncthreads();  // every warp has drained the accumulator and the A tile may be overwritten
-    tc_fence_after();
   }
-  if (warp == 0) tmem_dealloc(tmem, 32);
+  mbar_wait(&bar_mma, 1);
+  tc_fence_after();
+  // ---- epilogue: thread `row` of warp w (w % 4 selects the 32-lane TMEM slice) owns accumulator row `row` of its tile
+  const uint32_t trow = tmem + tile * 32 + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 16) {
+    float v[16];
+    tmem_ld16(trow + c0, v);
+    if (valid) {
+      uint32_t o[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        o[k] = pack_bf16(fmaxf(v[2 * k] * a.scale + sbias[c0 + 2 * k], 0.0f), fmaxf(v[2 * k + 1] * a.scale + sbias[c0 + 2 * k + 1], 0.0f));
+      uint4* out = reinterpret_cast<uint4*>(a.out + ((size_t)n * per + p) * 32 + c0);
+      out[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      out[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -785,7 +793,7 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     if (image_kernel) {
       // one image per CTA, planes staged by a bulk copy (k_conv1_image); any other observation shape takes the generic layer
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(n); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C1_SMEM; cfg.stream = st;
+      cfg.gridDim = dim3(n); cfg.blockDim = dim3(C1_THREADS); cfg.dynamicSmemBytes = C1_SMEM; cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
