@@ -366,7 +366,8 @@ struct SimBuffers {
   float* reset_record;  // [ST_STRIDE] state + [IN_STRIDE] info + [RS_STRIDE] render state of a freshly reset environment
   float* debug;         // [N][DEBUG_STRIDE]
   int* queue;           // [0] work-queue counter, [1..2] bucket counters of the longest-first order, [3] finished environments,
-                        // [4] observation tickets handed out, [5] blocks that left the fused kernel
+                        // [4] observation tickets handed out, [5] blocks that left the fused kernel, [6] blocks that started,
+                        // [16..63] class sizes / cursors of the queue order
   int* done_list;       // [N] environment ids in the order their agent steps finished (-1 = not yet); fused observation phase
   int* episode_count;   // [N] resets taken so far (reset randomisation: the hash counter)
   float* reset_obj;     // [N][12] pose (pos 3, mat 9) of the object geom at the start of the current episode (reset randomisation)

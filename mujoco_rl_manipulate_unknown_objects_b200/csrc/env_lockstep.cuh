@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
   unsigned smid = 0;
   if (FUSED && threadIdx.x == 0) {
     atomicMin(s.tstamp, global_ns());
+    atomicAdd(s.queue + 6, 1);  // blocks of this launch that are resident (render_phase)
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     atomicAdd(s.sm_phys + (smid & 255), 1);
   }

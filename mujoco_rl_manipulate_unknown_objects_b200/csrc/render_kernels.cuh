@@ -543,7 +543,19 @@ __device__ __forceinline__ void render_phase(const RenderScene& sc, const ObsArg
       // yield to a sibling block of this SM that is still integrating substeps: the kernel's duration is the longest substep
       // chain, and rasterising next to it would slow exactly that chain (sm_busy is only meaningful to thread 0's SM)
       while (*reinterpret_cast<volatile int*>(sm_busy) > 0) __nanosleep(2000);
-      const int ticket = atomicAdd(s.queue + 4, 1);
+      // Spinning on a ticket is only safe when the environment behind it is being integrated by a RESIDENT block.  The launch
+      // sizes the grid to what fits, but should a block still be waiting for an SM (GPU shared with another context), take
+      // only tickets whose environment has already finished, and leave when there is none: the late blocks render the rest.
+      int ticket;
+      if (*reinterpret_cast<volatile int*>(s.queue + 6) >= (int)gridDim.x) {
+        ticket = atomicAdd(s.queue + 4, 1);
+      } else {
+        for (;;) {
+          ticket = *reinterpret_cast<volatile int*>(s.queue + 4);
+          if (ticket >= *reinterpret_cast<volatile int*>(s.queue + 3)) { ticket = s.n; break; }
+          if (atomicCAS(s.queue + 4, ticket, ticket + 1) == ticket) break;
+        }
+      }
       int env = -1;
       if (ticket < s.n) {
         volatile int* slot = s.done_list + ticket;
