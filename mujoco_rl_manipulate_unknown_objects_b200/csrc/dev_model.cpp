@@ -3,6 +3,7 @@
 // Besides the plain copies this precomputes what the warp-per-environment kernels index by lane:
 // depth levels of the kinematic tree, subtree / ancestor bit masks, and the per-pair contact parameters
 // that MuJoCo's mj_contactParam (engine_collision_driver.c) mixes from the two geoms at run time.
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <stdexcept>
@@ -23,6 +24,7 @@ void build_dev_model(const HostModel& h, DevModel& d, std::vector<float>& hv4, s
   d.nbody = h.nbody; d.njnt = h.njnt; d.ngeom = h.ngeom; d.npair = h.npair; d.iterations = h.iterations; d.ncam = h.ncam;
   d.timestep = (float)h.timestep; d.impratio = (float)h.impratio; d.meaninertia = (float)h.meaninertia;
   d.solver_scale = (float)(1.0 / (h.meaninertia * std::max(1, h.nv)));
+  d.newton_noise = getenv("GRS_NEWTON_NOISE") ? (float)atof(getenv("GRS_NEWTON_NOISE")) : 3.6e-7f;  // 3 ulps: iteration counts close to the fp64 oracle (tools/iter_compare.py: 1.2 vs 1.1), parity statistics unchanged
   for (int k = 0; k < 3; k++) d.gravity[k] = (float)h.gravity[k];
   d.xfrc_ee_z = (float)(-(0.438 * h.gravity[2]));  // robot_env.py:64-65
   // depth levels

@@ -1129,6 +1129,14 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
     float gn = scale * sqrtf(warp_sum(g * g));
     if (gn < tol) break;
     if (iter > 0 && improvement < tol) break;
+    if (iter > 0 && m.newton_noise > 0.0f) {
+      // fp32 resolution of the gradient: g = Ma - fsmooth - J^T f is a difference of terms of magnitude |Ma| + |fsmooth| + |J^T f|,
+      // each carrying a few ulps of rounding noise.  Once a Newton step has brought the gradient down to that noise floor a
+      // further iteration cannot improve the solution (the fp64 oracle, whose floor is 1e-9 of this, stops here with
+      // gradient < tolerance; tools/iter_compare.py: 1.1 vs 2.15 iterations per substep before this test).
+      const float mag = lane < NV ? fabsf(w.Ma[lane]) + fabsf(w.fsmooth[lane]) + fabsf(fc) : 0.0f;
+      if (gn < m.newton_noise * scale * sqrtf(warp_sum(mag * mag))) break;
+    }
     __syncwarp();
     make_hessian(w, lane);
     float s = w.coupled ? chol_factor_solve<false>(w.u.con.H, w.cho, -g, lane) : chol_factor_solve<true>(w.u.con.H, w.cho, -g, lane);
