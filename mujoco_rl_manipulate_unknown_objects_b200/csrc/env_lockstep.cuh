@@ -3,12 +3,16 @@
 // The sequential kernel (k_env_step in env_kernels.cuh) lets every warp run its own environment's state machine
 // freely.  Profiling showed it to be INSTRUCTION-FETCH bound: ~120 KB of hot code per substep, 20 warps per SM at
 // unrelated program counters, 58 % hit rate in the 32 KB SM instruction cache and half of all issue slots lost to
-// "no instruction" stalls (profiles/r1_env_step_sequential.md).  Here all warps of a block walk the substep pipeline
+// "no instruction" stalls.  Here all warps of a block walk the substep pipeline
 // TOGETHER — smooth forces | constraint rows | Newton solve | integrate + kinematics | CRB | collision — with a block
 // barrier between the stages, so the SM's instruction cache only ever holds one stage's code.  The per-environment
 // controller state machine (reference robot_env.py:77-241) becomes an explicit `tick` that runs between rounds and
 // decides, per warp, whether this round carries a physics substep; environments still come from the atomic queue, so
 // ragged trip counts only cost idle warps inside a round, never idle rounds.
+//
+// Around that core: k_order_count / k_order_envs queue the environments longest chain first and group them by contact count;
+// a block whose physics work is exhausted becomes an observation builder (render_phase) for the environments that have
+// already finished; the physics phase is timed on the device (%globaltimer).
 #pragma once
 #include "env_kernels.cuh"
 #include "render_kernels.cuh"
@@ -224,9 +228,6 @@ __global__ void k_order_envs(SimBuffers s, const float* __restrict__ actions, in
   s.done_list[env] = -1;
 }
 
-#ifndef LS_BARRIERS
-#define LS_BARRIERS 4
-#endif
 constexpr int LS_MAX_THREADS = 512;  // 16 warps: leaves 128 registers per thread (2 blocks of 8 warps per SM in production)
 
 // TIMING = true: per-stage clock64 bookkeeping (sum over warps vs. per-round block maximum) into s.debug — a development
