@@ -64,3 +64,30 @@ def test_no_cpu_fallback():
     lib = _native.load()
     assert lib.grs_create(b"x.xml", 2, None, 0) is None and b"CUDA" in lib.grs_last_error()
     assert lib.grp_create(2, 5, 64, 64, 6, 0) is None and b"CUDA" in lib.grp_last_error()
+
+
+def test_config_struct_layout_is_the_same_in_header_binding_and_integration_stub():
+    """grs_config is passed by pointer: the header, the package's ctypes binding and the stub shown in INTEGRATION.md must list the
+    same fields in the same order with the same types, and the defaults of the trailing (non-reference) fields must be neutral."""
+    from mujoco_rl_manipulate_unknown_objects_b200 import _native
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct grs_config \{(.*?)\} grs_config;", src, flags=re.S).group(1)
+    header = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        header += [(n.strip(), ctype) for n in names.split(",")]
+    ctype_of = {C.c_int32: "int32_t", C.c_float: "float", C.c_uint32: "uint32_t"}
+    binding = [(n, ctype_of[t]) for n, t in _native.GrsConfig._fields_]
+    assert header == binding
+    assert C.sizeof(_native.GrsConfig) == 4 * len(header)
+    stub = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = stub[stub.index("class GrsConfig(C.Structure)"):stub.index("lib.grs_create.restype")]
+    pos = [stub.index('"%s"' % n) for n, _ in header]  # every field named, in declaration order
+    assert pos == sorted(pos)
+    lib = _native.load()
+    c = _native.GrsConfig()
+    lib.grs_default_config(C.byref(c))
+    assert (c.reset_noise_xy, c.reset_noise_yaw, c.seed) == (0.0, 0.0, 0)  # the reference's deterministic reset
