@@ -91,3 +91,22 @@ def test_config_struct_layout_is_the_same_in_header_binding_and_integration_stub
     c = _native.GrsConfig()
     lib.grs_default_config(C.byref(c))
     assert (c.reset_noise_xy, c.reset_noise_yaw, c.seed) == (0.0, 0.0, 0)  # the reference's deterministic reset
+
+
+def test_info_record_layout_matches_the_header():
+    """The packed per-environment step record: the header's GRS_INFO_* enum (evaluated like a C compiler would) against the
+    indices the Python layer uses to build `infos`."""
+    from mujoco_rl_manipulate_unknown_objects_b200 import _native
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"enum \{\s*(GRS_INFO_REWARD.*?)\};", src, flags=re.S).group(1)
+    values, nxt = {}, 0
+    for item in body.split(","):
+        item = item.strip()
+        if not item:
+            continue
+        name, _, val = item.partition("=")
+        nxt = int(val) if val.strip() else nxt
+        values[name.strip()[len("GRS_INFO_"):]] = nxt
+        nxt += 1
+    assert values == _native.INFO
+    assert _native.INFO["STRIDE"] == 40 and _native.STATE_STRIDE == 64 and _native.RENDER_STATE_STRIDE == 96
