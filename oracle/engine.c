@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define MINVAL 1e-15
 
@@ -125,6 +126,16 @@ int orc_set_d(OModel *m, const char *name, const double *v, int n) {
   FIELD_D(geom_rbound, O_MAXG) FIELD_D(geom_size, O_MAXG * 3) FIELD_D(act_gear, O_MAXU) FIELD_D(act_ctrlrange, O_MAXU * 2)
   FIELD_D(body_invweight0, O_MAXB * 2) FIELD_D(dof_invweight0, O_MAXV) SCALAR_D(meaninertia)
   return -1;
+}
+/* read back what orc_model_finalize derived (tests/test_model_compiler.py compares it with the product compiler) */
+int orc_get_d(const OModel *m, const char *name, double *out, int n) {
+  const double *src = NULL; int cap = 0;
+  if (!strcmp(name, "body_invweight0")) { src = m->body_invweight0; cap = 2 * m->nbody; }
+  else if (!strcmp(name, "dof_invweight0")) { src = m->dof_invweight0; cap = m->nv; }
+  else if (!strcmp(name, "meaninertia")) { src = &m->meaninertia; cap = 1; }
+  if (!src || n < cap) return -1;
+  memcpy(out, src, cap * sizeof(double));
+  return cap;
 }
 #define FIELD_I(nm, cap) if (!strcmp(name, #nm)) { if (n > (cap)) return -2; memcpy(m->nm, v, n * sizeof(int)); return 0; }
 #define SCALAR_I(nm) if (!strcmp(name, #nm)) { m->nm = v[0]; return 0; }
@@ -1465,24 +1476,60 @@ void orc_env_step(OEnv *e, const double *action, OStepOut *out) {
 typedef struct {
   const OModel *m; const OEnvCfg *cfg; int body_ee, body_object; const int *f1, *f2;
   int env0, env1, nsteps; const double *actions; double reward; long substeps, transitions;
+  int skip; double timed_seconds; long ncon_sum; /* skip: leading transitions per env that are rolled but not counted or timed */
 } Job;
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 static void *rollout_worker(void *arg) {
   Job *j = (Job *)arg;
   for (int e = j->env0; e < j->env1; e++) {
     OEnv *env = orc_env_new(j->m, j->cfg, j->body_ee, j->body_object, j->f1, j->f2);
     OStepOut out;
     orc_env_reset(env, &out);
+    long sub0 = 0;
+    double t0 = now_s();
     for (int s = 0; s < j->nsteps; s++) {
+      if (s == j->skip) { sub0 = env->total_substeps; t0 = now_s(); }
       orc_env_step(env, j->actions + ((size_t)e * j->nsteps + s) * 6, &out);
-      j->reward += out.reward;
-      j->transitions++;
+      if (s >= j->skip) { j->reward += out.reward; j->transitions++; j->ncon_sum += env->d->ncon; }
       if (out.done) orc_env_reset(env, NULL);
     }
-    j->substeps += env->total_substeps;
+    if (j->nsteps > j->skip) { j->timed_seconds += now_s() - t0; j->substeps += env->total_substeps - sub0; }
     orc_env_free(env);
   }
   return NULL;
 }
+/* the same with a window: every env rolls `skip` transitions from reset first (not counted, not timed), then nsteps - skip
+ * counted ones.  *timed_seconds = max over threads of the time each spent inside its counted windows (all threads busy
+ * throughout), *ncon_sum = sum over counted transitions of the contact count at the end of the transition. */
+long orc_rollout_window(const OModel *m, const OEnvCfg *cfg, int body_ee, int body_object, const int *finger1, const int *finger2,
+                        int nenv, int nsteps, int skip, const double *actions, int nthreads, double *reward_sum, long *transitions,
+                        double *timed_seconds, long *ncon_sum) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > nenv) nthreads = nenv;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+  Job *jobs = (Job *)calloc(nthreads, sizeof(Job));
+  for (int t = 0; t < nthreads; t++) {
+    Job *j = &jobs[t];
+    j->m = m; j->cfg = cfg; j->body_ee = body_ee; j->body_object = body_object; j->f1 = finger1; j->f2 = finger2;
+    j->env0 = (int)((long)nenv * t / nthreads); j->env1 = (int)((long)nenv * (t + 1) / nthreads);
+    j->nsteps = nsteps; j->skip = skip; j->actions = actions;
+    pthread_create(&th[t], NULL, rollout_worker, j);
+  }
+  long sub = 0, tr = 0, nc = 0;
+  double rs = 0, ts = 0;
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    sub += jobs[t].substeps; tr += jobs[t].transitions; rs += jobs[t].reward; nc += jobs[t].ncon_sum;
+    if (jobs[t].timed_seconds > ts) ts = jobs[t].timed_seconds;
+  }
+  if (reward_sum) *reward_sum = rs;
+  if (transitions) *transitions = tr;
+  if (timed_seconds) *timed_seconds = ts;
+  if (ncon_sum) *ncon_sum = nc;
+  free(th); free(jobs);
+  return sub;
+}
+
 long orc_rollout_threads(const OModel *m, const OEnvCfg *cfg, int body_ee, int body_object, const int *finger1, const int *finger2,
                          int nenv, int nsteps, const double *actions, int nthreads, double *reward_sum, long *transitions) {
   if (nthreads < 1) nthreads = 1;

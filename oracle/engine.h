@@ -112,6 +112,7 @@ OModel *orc_model_new(void);
 void orc_model_free(OModel *m);
 int orc_set_d(OModel *m, const char *name, const double *v, int n);
 int orc_set_i(OModel *m, const char *name, const int *v, int n);
+int orc_get_d(const OModel *m, const char *name, double *out, int n); /* body_invweight0 | dof_invweight0 | meaninertia */
 int orc_set_mesh(OModel *m, int id, int nvert, const double *vert, const int *adjadr, const int *adj);
 void orc_model_finalize(OModel *m); /* body_rootid, invweight0, meaninertia at qpos0 */
 
@@ -158,6 +159,10 @@ int orc_pheromone_level(const OEnv *e);
 double orc_agent_reward(const double *init_obj, const double *final_obj, const double *dir, int gripper_open,
                         const double *controls, int grasped);
 
+/* windowed variant: `skip` leading transitions per env are rolled but neither counted nor timed (bench.py reference arm) */
+long orc_rollout_window(const OModel *m, const OEnvCfg *cfg, int body_ee, int body_object, const int *finger1, const int *finger2,
+                        int nenv, int nsteps, int skip, const double *actions, int nthreads, double *reward_sum, long *transitions,
+                        double *timed_seconds, long *ncon_sum);
 /* rollout of many independent envs on host threads: the CPU baseline of bench.py */
 long orc_rollout_threads(const OModel *m, const OEnvCfg *cfg, int body_ee, int body_object, const int *finger1,
                          const int *finger2, int nenv, int nsteps, const double *actions /* nenv*nsteps*6 */,

@@ -85,6 +85,7 @@ def lib():
         L.orc_model_free.argtypes = [C.c_void_p]
         L.orc_set_d.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
         L.orc_set_i.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
+        L.orc_get_d.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
         L.orc_set_mesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_model_finalize.argtypes = [C.c_void_p]
         L.orc_data_new.restype = C.POINTER(OData)
@@ -106,6 +107,9 @@ def lib():
         L.orc_rollout_threads.restype = C.c_long
         L.orc_rollout_threads.argtypes = [C.c_void_p, C.POINTER(OEnvCfg), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
+        L.orc_rollout_window.restype = C.c_long
+        L.orc_rollout_window.argtypes = [C.c_void_p, C.POINTER(OEnvCfg), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double), C.POINTER(C.c_long)]
         _LIB = L
     return _LIB
 
@@ -157,6 +161,13 @@ class Model:
 
     def body_id(self, name):
         return self.md["body_names"].index(name)
+
+    def derived(self, name):
+        """body_invweight0 / dof_invweight0 / meaninertia as computed by orc_model_finalize (mj_setConst)."""
+        out = np.zeros(64)
+        n = lib().orc_get_d(self.ptr, name.encode(), out.ctypes.data, out.size)
+        assert n > 0, name
+        return out[:n].copy()
 
     def __del__(self):
         try:
@@ -329,3 +340,15 @@ def rollout_threads(model, actions, nthreads, **cfg):
     sub = lib().orc_rollout_threads(model.ptr, C.byref(c), model.body_id("ee"), model.body_id("object"), f1.ctypes.data,
                                     f2.ctypes.data, a.shape[0], a.shape[1], a.ctypes.data, nthreads, C.byref(rs), C.byref(tr))
     return sub, tr.value, rs.value
+
+
+def rollout_window(model, actions, nthreads, skip, **cfg):
+    """actions: [nenv, nsteps, 6] float64; the first `skip` transitions of every env are rolled from reset but neither counted
+    nor timed.  Returns dict(substeps, transitions, reward_sum, seconds, ncon_sum) over the counted window."""
+    c = default_cfg(**cfg)
+    f1, f2 = _finger_ids(model)
+    a = np.ascontiguousarray(actions, dtype=np.float64)
+    rs, tr, ts, nc = C.c_double(0), C.c_long(0), C.c_double(0), C.c_long(0)
+    sub = lib().orc_rollout_window(model.ptr, C.byref(c), model.body_id("ee"), model.body_id("object"), f1.ctypes.data, f2.ctypes.data,
+                                   a.shape[0], a.shape[1], int(skip), a.ctypes.data, nthreads, C.byref(rs), C.byref(tr), C.byref(ts), C.byref(nc))
+    return dict(substeps=sub, transitions=tr.value, reward_sum=rs.value, seconds=ts.value, ncon_sum=nc.value)

@@ -275,8 +275,8 @@ def compile_mjcf(xml_path):
         g["friction"] = base
         rgba = np.array([0.5, 0.5, 0.5, 1.0])
         mat = materials.get(a.get("material", ""), None)
-        if mat is not None and "rgba" in mat:
-            rgba = _floats(mat["rgba"])
+        if mat is not None:          # effective render colour: a material replaces the geom default; <material rgba> defaults to "1 1 1 1"
+            rgba = _floats(mat.get("rgba", "1 1 1 1"))
         if "rgba" in a:
             rgba = _floats(a["rgba"])
         g["rgba"] = rgba
