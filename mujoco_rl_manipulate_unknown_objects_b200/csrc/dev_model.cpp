@@ -24,6 +24,7 @@ void build_dev_model(const HostModel& h, DevModel& d, std::vector<float>& hv4, s
   d.nbody = h.nbody; d.njnt = h.njnt; d.ngeom = h.ngeom; d.npair = h.npair; d.iterations = h.iterations; d.ncam = h.ncam;
   d.timestep = (float)h.timestep; d.impratio = (float)h.impratio; d.meaninertia = (float)h.meaninertia;
   d.solver_scale = (float)(1.0 / (h.meaninertia * std::max(1, h.nv)));
+  d.gap_skip = getenv("GRS_GAP_SKIP") ? atoi(getenv("GRS_GAP_SKIP")) : 1;
   d.newton_noise = getenv("GRS_NEWTON_NOISE") ? (float)atof(getenv("GRS_NEWTON_NOISE")) : 3.6e-7f;  // 3 ulps: iteration counts close to the fp64 oracle (tools/iter_compare.py: 1.2 vs 1.1), parity statistics unchanged
   for (int k = 0; k < 3; k++) d.gravity[k] = (float)h.gravity[k];
   d.xfrc_ee_z = (float)(-(0.438 * h.gravity[2]));  // robot_env.py:64-65

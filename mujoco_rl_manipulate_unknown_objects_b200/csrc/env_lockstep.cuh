@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s,
       // first environment of a warp: static slot, so that a block starts with consecutive queue entries (environments of the
       // same class, see k_order_envs); later ones come from the shared counter, which starts behind the static slots
       const int nstatic = gridDim.x * (blockDim.x >> 5);
-      int slot = first ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : nstatic + next_env(s.queue, lane);
+      int slot = first ? (s.slot_order ? (threadIdx.x >> 5) * gridDim.x + blockIdx.x : blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))
+                       : nstatic + next_env(s.queue, lane);
       first = false;
       if (slot < s.n) {
         const int env = __ldg(s.order + slot);

@@ -158,6 +158,7 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     b.ls_mask = 22;
     b.order_ncon = getenv("GRS_ORDER_NCON") ? atoi(getenv("GRS_ORDER_NCON")) : 0;
     if (const char* e = getenv("GRS_LS_MASK")) b.ls_mask = atoi(e);
+    b.slot_order = getenv("GRS_SLOT_ORDER") ? atoi(getenv("GRS_SLOT_ORDER")) : 0;
     b.order = dalloc<int>(s.get(), N);
     const size_t obs_bytes = (size_t)s->C * s->H * s->W;
     s->d_obs = dalloc<unsigned char>(s.get(), N * obs_bytes);
@@ -223,9 +224,13 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     ObsArgs& oa = s->obs_args;
     oa.obs = s->d_obs; oa.terminal_obs = s->d_terminal_obs; oa.reset_obs = s->d_reset_obs; oa.hist_prev = s->d_hist; oa.hist_reset = s->d_hist + N * 512;
     oa.C = s->C; oa.H = s->H; oa.W = s->W; oa.fovy = (float)s->hm.cam_fovy[e.obs_cam]; oa.auto_reset = e.auto_reset; oa.im_reward = e.im_reward;
+    oa.obs_host = nullptr; oa.terminal_obs_host = nullptr;
+    oa.info = s->b.info; oa.state = s->b.state; oa.info_stride = IN_STRIDE; oa.state_stride = ST_STRIDE;
+    oa.in_reward = IN_REWARD; oa.in_ep_return = IN_EPISODE_RETURN; oa.st_ep_return = ST_EP_RETURN;
     {
       ObsArgs r = oa;  // the reset image: one environment, no previous histograms (they go to hist_reset), no reward
       r.obs = s->d_reset_obs; r.terminal_obs = nullptr; r.reset_obs = nullptr; r.hist_prev = nullptr; r.auto_reset = 0; r.im_reward = 0;
+      r.info = nullptr; r.state = nullptr;
       launch_render_obs(s->scene, r, s->b.reset_record + ST_STRIDE + IN_STRIDE, s->b.reset_record + ST_STRIDE, nullptr, nullptr, 1, s->stream);
     }
     s->launches++;
@@ -319,6 +324,16 @@ extern "C" int32_t grs_step(grs_sim* s, const float* actions_dev, void* stream) 
   } catch (const std::exception& e) { return fail(e.what()); }
 }
 
+// Device-visible address of a caller's host buffer if it is page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch's
+// pin_memory()): the observation phase then stores finished observations straight into it.  NULL for pageable memory.
+static unsigned char* mapped_host_ptr(void* host) {
+  if (!host || getenv("GRS_NO_HOST_MIRROR")) return nullptr;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return (unsigned char*)a.devicePointer;
+}
+
 extern "C" int32_t grs_step_host(grs_sim* s, const float* actions_host, uint8_t* obs_host, float* achieved_host, float* desired_host,
                                  float* reward_host, uint8_t* done_host, float* info_host, uint8_t* terminal_obs_host) {
   GUARD(s);
@@ -327,17 +342,39 @@ extern "C" int32_t grs_step_host(grs_sim* s, const float* actions_host, uint8_t*
     CU(cudaSetDevice(s->device));
     const size_t N = s->n, ob = (size_t)s->C * s->H * s->W;
     CU(cudaMemcpyAsync(s->d_actions, actions_host, N * s->adim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    if (grs_step(s, s->d_actions, nullptr) != 0) return 1;
-    if (obs_host) CU(cudaMemcpyAsync(obs_host, s->d_obs, N * ob, cudaMemcpyDeviceToHost, s->stream));
+    // pinned destination buffers are written by the observation phase itself, environment by environment as their agent
+    // steps finish (render_kernels.cuh : mirror_to_host): no bulk copy of the images after the kernel
+    unsigned char* obs_m = mapped_host_ptr(obs_host);
+    unsigned char* tobs_m = mapped_host_ptr(terminal_obs_host);
+    s->obs_args.obs_host = obs_m; s->obs_args.terminal_obs_host = tobs_m;
+    const int rc = grs_step(s, s->d_actions, nullptr);
+    s->obs_args.obs_host = nullptr; s->obs_args.terminal_obs_host = nullptr;
+    if (rc != 0) return 1;
+    std::vector<uint8_t> done_tmp;
+    uint8_t* dn = done_host;
+    if (terminal_obs_host && !tobs_m && !dn) { done_tmp.resize(N); dn = done_tmp.data(); }
+    if (dn) CU(cudaMemcpyAsync(dn, s->b.done, N, cudaMemcpyDeviceToHost, s->stream));
+    if (obs_host && !obs_m) CU(cudaMemcpyAsync(obs_host, s->d_obs, N * ob, cudaMemcpyDeviceToHost, s->stream));
     if (achieved_host) CU(cudaMemcpyAsync(achieved_host, s->b.achieved, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     if (desired_host) CU(cudaMemcpyAsync(desired_host, s->b.desired, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     if (reward_host) CU(cudaMemcpyAsync(reward_host, s->b.reward, N * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    if (done_host) CU(cudaMemcpyAsync(done_host, s->b.done, N, cudaMemcpyDeviceToHost, s->stream));
     if (info_host) CU(cudaMemcpyAsync(info_host, s->b.info, N * IN_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    if (terminal_obs_host) CU(cudaMemcpyAsync(terminal_obs_host, s->d_terminal_obs, N * ob, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    if (terminal_obs_host && !tobs_m) {
+      // terminal observations exist only for environments whose episode ended in this step: copy those rows alone
+      // (rows of the other environments are left untouched)
+      size_t nd = 0;
+      for (size_t e = 0; e < N; e++) nd += dn[e] != 0;
+      if (nd * 8 > N) {
+        CU(cudaMemcpyAsync(terminal_obs_host, s->d_terminal_obs, N * ob, cudaMemcpyDeviceToHost, s->stream));
+      } else {
+        for (size_t e = 0; e < N; e++)
+          if (dn[e]) CU(cudaMemcpyAsync(terminal_obs_host + e * ob, s->d_terminal_obs + e * ob, ob, cudaMemcpyDeviceToHost, s->stream));
+      }
+      if (nd) CU(cudaStreamSynchronize(s->stream));
+    }
     return 0;
-  } catch (const std::exception& e) { return fail(e.what()); }
+  } catch (const std::exception& e) { s->obs_args.obs_host = nullptr; s->obs_args.terminal_obs_host = nullptr; return fail(e.what()); }
 }
 
 extern "C" int32_t grs_reset_host(grs_sim* s, uint8_t* obs_host, float* achieved_host, float* desired_host) {

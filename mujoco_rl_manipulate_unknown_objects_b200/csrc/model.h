@@ -68,6 +68,7 @@ HostModel compile_mjcf(const std::string& xml_path);
 struct DevModel {
   int nbody, njnt, ngeom, npair, nlevel, nhv_total, iterations, ncam;
   float timestep, impratio, meaninertia, solver_scale;
+  int gap_skip;        // collision: skip convex pairs whose cached separating axis provably still separates them (exact; GRS_GAP_SKIP=0 disables)
   float newton_noise;  // gradient noise floor of the fp32 Newton solver, in units of |Ma| + |fsmooth| + |J^T f| (0 = test disabled)
   float gravity[3], xfrc_ee_z;  // xfrc_ee_z = 0.438*9.81, robot_env.py:64-65
   // bodies, stored in level order is NOT assumed: level_body lists body ids per depth level

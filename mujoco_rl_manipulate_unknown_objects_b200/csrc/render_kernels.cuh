@@ -394,7 +394,29 @@ struct ObsArgs {
   const float* reset_rs;   // [RS_STRIDE] render state of the reset record
   const float* reset_obj;  // [n][12] object geom pose of each environment's current episode
   unsigned char reset_pad0, reset_pad1;  // pad-channel scalars of a freshly reset environment
+  // host mirrors (grs_step_host with PINNED host buffers): device-visible addresses of the caller's pinned observation /
+  // terminal-observation arrays, or NULL.  Each finished observation is stored there by the block that built it, so the
+  // device-to-host transfer of the 20 KB images rides under the physics of the environments still integrating.
+  unsigned char* obs_host;
+  unsigned char* terminal_obs_host;
+  // intrinsic reward bookkeeping (reward.py:51-55 adds the KL term to the step reward, which robot_env.py:199 sums into
+  // the episode): per-env info rows and state records, with the slots the term has to reach
+  float* info;
+  float* state;
+  int info_stride, state_stride, in_reward, in_ep_return, st_ep_return;
 };
+
+// copy `bytes` of an observation this block has just written to global memory into the caller's pinned host array
+__device__ __forceinline__ void mirror_to_host(const unsigned char* src, unsigned char* dst_host, int bytes) {
+  __syncthreads();  // the block's own stores to `src` are visible to the block
+  if ((bytes & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst_host);
+    for (int i = threadIdx.x; i < bytes / 16; i += RTHREADS) d4[i] = __ldcg(s4 + i);
+  } else {
+    for (int i = threadIdx.x; i < bytes; i += RTHREADS) dst_host[i] = __ldcg(src + i);
+  }
+}
 
 // Observation of ONE environment by one block of RTHREADS threads (the observation is a single tile, W,H <= 64):
 // rasterise + shade (render_tile), transform_depth, uint8 CHW packing with the two scalar channels, histograms, intrinsic
@@ -460,8 +482,13 @@ __device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsA
   const unsigned char* reset_obs = o.reset_obs;
   float* hist_prev = o.hist_prev;
   float* hist_reset = o.hist_reset;
-  unsigned char* dst = (is_done && auto_reset) ? o.terminal_obs + (size_t)env * C * npix : obs + (size_t)env * C * npix;
+  const bool swap = is_done && auto_reset;
+  unsigned char* dst = swap ? o.terminal_obs + (size_t)env * C * npix : obs + (size_t)env * C * npix;
   render_and_pack(sc, o, rs, dst, pad0, pad1, sh, rgb8);
+  {
+    unsigned char* hm = swap ? o.terminal_obs_host : o.obs_host;
+    if (hm) mirror_to_host(dst, hm + (size_t)env * C * npix, C * npix);
+  }
   // intrinsic reward (reward.py:57-77): KL(old || new) of the grey (and depth) histograms, float32 pdfs
   float* hp = hist_prev ? hist_prev + (size_t)env * 512 : nullptr;
   if (im_reward && reward && hp) {
@@ -474,7 +501,16 @@ __device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsA
     }
     kl_g = block_reduce(kl_g, sh.red, 0);
     kl_d = block_reduce(kl_d, sh.red, 0);
-    if (tid == 0) reward[env] = __ldcg(reward + env) + (C == 5 ? 0.5f * (kl_g + kl_d) : kl_g);
+    if (tid == 0) {
+      const float kl = C == 5 ? 0.5f * (kl_g + kl_d) : kl_g;
+      reward[env] = __ldcg(reward + env) + kl;
+      if (o.info) {  // the info record's reward / Monitor return and the running episode return carry the term as well
+        float* inf = o.info + (size_t)env * o.info_stride;
+        inf[o.in_reward] = __ldcg(inf + o.in_reward) + kl;
+        inf[o.in_ep_return] = __ldcg(inf + o.in_ep_return) + kl;
+        if (o.state && !swap) { float* st = o.state + (size_t)env * o.state_stride; st[o.st_ep_return] = __ldcg(st + o.st_ep_return) + kl; }
+      }
+    }
   }
   __syncthreads();
   if (is_done && auto_reset) {
@@ -482,12 +518,18 @@ __device__ __forceinline__ void render_obs_env(const RenderScene& sc, const ObsA
     if (o.reset_noise) {
       build_reset_scene(o, env, rs2);
       render_and_pack(sc, o, rs2, obs + (size_t)env * C * npix, o.reset_pad0, o.reset_pad1, sh, rgb8);
+      if (o.obs_host) mirror_to_host(obs + (size_t)env * C * npix, o.obs_host + (size_t)env * C * npix, C * npix);
       if (hp) for (int i = tid; i < 512; i += RTHREADS) hp[i] = (float)(&sh.hist[0][0])[i];
     } else {
       const uint4* src = reinterpret_cast<const uint4*>(reset_obs);
       uint4* o4 = reinterpret_cast<uint4*>(obs + (size_t)env * C * npix);
       if ((C * npix) % 16 == 0) { for (int i = tid; i < C * npix / 16; i += RTHREADS) o4[i] = src[i]; }
       else { for (int i = tid; i < C * npix; i += RTHREADS) obs[(size_t)env * C * npix + i] = reset_obs[i]; }
+      if (o.obs_host) {
+        unsigned char* oh = o.obs_host + (size_t)env * C * npix;
+        if ((C * npix) % 16 == 0) { uint4* h4 = reinterpret_cast<uint4*>(oh); for (int i = tid; i < C * npix / 16; i += RTHREADS) h4[i] = src[i]; }
+        else { for (int i = tid; i < C * npix; i += RTHREADS) oh[i] = reset_obs[i]; }
+      }
       if (hp) for (int i = tid; i < 512; i += RTHREADS) hp[i] = hist_reset[i];
     }
   } else {
@@ -580,7 +622,10 @@ __device__ __forceinline__ void render_phase(const RenderScene& sc, const ObsArg
 inline void launch_render_obs(const RenderScene& sc, const ObsArgs& o, const float* render_state, const float* info, const unsigned char* done, float* reward, int n,
                               cudaStream_t st) {
   if (o.W > TILE || o.H > TILE) throw std::runtime_error("observation size above 64x64 is not supported by the fused observation kernel");
-  static bool attr = false;
+  static bool attr_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr = attr_dev[dev_ & 63];  // the attribute is per device: a second simulator on another GPU of this process needs it too
   if (!attr) {
     if (cudaFuncSetAttribute(k_render_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_phase_smem_bytes()) != cudaSuccess) throw std::runtime_error("cudaFuncSetAttribute(k_render_obs)");
     if (cudaFuncSetAttribute(k_render_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_phase_smem_bytes()) != cudaSuccess) throw std::runtime_error("cudaFuncSetAttribute(k_render_reset)");
@@ -629,7 +674,10 @@ __global__ void __launch_bounds__(RTHREADS) k_render_raw(RenderScene sc, const f
 }
 inline void launch_render_raw(const RenderScene& sc, const float* render_state, int rs_stride, unsigned char* rgb, float* depth, int n, int H, int W, double fovy,
                               cudaStream_t st) {
-  static bool attr = false;
+  static bool attr_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr = attr_dev[dev_ & 63];
   if (!attr) {
     if (cudaFuncSetAttribute(k_render_raw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)render_smem_bytes()) != cudaSuccess) throw std::runtime_error("cudaFuncSetAttribute(k_render_raw)");
     attr = true;

@@ -46,6 +46,8 @@ struct __align__(16) WS {
   float sup[5][9];  // MPR portal (collision)
   float cho[16];    // Cholesky right-hand side / solution exchange
   float sep[MAXPAIR][3];  // last separating direction found for each convex pair (zero = none); temporal coherence only
+  float gapb[MAXPAIR];    // separation left along sep[p] after subtracting how far the two geoms can have moved since it was measured
+  float disp[MAXG];       // bound on the motion of any point of geom g during the last substep (kinematics)
   union {
     struct {  // smooth-dynamics scratch (dead once qfrc_bias is known)
       float xipos[MAXB][3], ximat[MAXB][9], cinert[MAXB][10], crb[MAXB][10], cdofdot[16][6], cvel[MAXB][6], cfrc[MAXB][6];
@@ -268,12 +270,16 @@ __device__ __noinline__ void kinematics(const DevModel& m, WS& w, int lane) {
   }
   if (lane < m.ngeom) {
     int g = lane, b = m.geom_body[g];
-    float t[3], q[4];
+    float t[3], q[4], R[9];
     mulmat3vec(t, w.xmat[b], m.geom_pos[g]);
-    for (int k = 0; k < 3; k++) w.gpos[g][k] = w.xpos[b][k] + t[k];
     quat_mul(q, w.xquat[b], m.geom_quat[g]);
     quat_normalize(q);
-    quat2mat(w.gmat[g], q);
+    quat2mat(R, q);
+    // how far any point of the geom can have moved since the previous pose: |dp| + rbound * |dR|_F  (collision: gapb)
+    float d2 = 0, r2 = 0;
+    for (int k = 0; k < 3; k++) { const float np_ = w.xpos[b][k] + t[k], d = np_ - w.gpos[g][k]; d2 += d * d; w.gpos[g][k] = np_; }
+    for (int k = 0; k < 9; k++) { const float d = R[k] - w.gmat[g][k]; r2 += d * d; w.gmat[g][k] = R[k]; }
+    w.disp[g] = sqrtf(d2) + m.geom_rbound[g] * sqrtf(r2);
   }
   __syncwarp();
 }
@@ -655,6 +661,16 @@ __device__ __noinline__ void collision(const DevModel& m, WS& w, const float4* h
     } else {
       const float bound = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
       cand = !(dot3(dif, dif) > bound * bound);
+      // Separation budget.  sep[p] separated the pair by gapb[p] when it was last evaluated; since then no point of either geom
+      // moved further than the disp[] bounds accumulated here, so while the budget stays positive sep[p] still separates
+      // them: the support evaluation below would say so and skip the pair — skip it without evaluating.  (NaN budgets,
+      // e.g. from the garbage pose of a freshly loaded workspace, compare false and fall through to the evaluation.)
+      if (m.gap_skip) {
+        const float left = w.gapb[lane] - (1.001f * (w.disp[g1] + w.disp[g2]) + 2e-7f);
+        w.gapb[lane] = left;
+        const bool has_axis = w.sep[lane][0] != 0.0f || w.sep[lane][1] != 0.0f || w.sep[lane][2] != 0.0f;
+        if (cand && has_axis && left > 0.0f) cand = false;
+      }
     }
   }
   unsigned todo = __ballot_sync(FULL, cand);
@@ -719,11 +735,19 @@ __device__ __noinline__ void collision(const DevModel& m, WS& w, const float4* h
       float ca[3] = {w.sep[p][0], w.sep[p][1], w.sep[p][2]};
       if (ca[0] != 0.0f || ca[1] != 0.0f || ca[2] != 0.0f) {
         support_md(m, w, hv, g1, g2, margin, ca, 4, lane);
-        if (dot3(SUPV(4), ca) < 0) continue;
+        const float sd = dot3(SUPV(4), ca);
+        if (sd < 0) {
+          // ca is a unit vector (mpr_penetration normalises what it returns): -sd is the separation along it, in metres
+          __syncwarp();
+          if (lane == 0) w.gapb[p] = -sd - 2e-6f;
+          __syncwarp();
+          continue;
+        }
       }
       bool hit = mpr_penetration(m, w, hv, g1, g2, margin, &depth, dir, pos, lane);
       __syncwarp();
       if (lane < 3) w.sep[p][lane] = hit ? 0.0f : dir[lane];
+      if (lane == 3) w.gapb[p] = 0.0f;  // a new axis (or none): its separation is measured by the next substep's support evaluation
       __syncwarp();
       if (!hit) continue;
       add_contact(m, w, p, margin - depth, pos, dir, lane);

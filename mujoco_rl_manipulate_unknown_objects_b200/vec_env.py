@@ -2,7 +2,7 @@
 holding thousands of RobotEnv instances on one GPU.
 
 Follows the stable-baselines3 VecEnv protocol (reset / step_async / step_wait / step, auto-reset with
-infos[i]["terminal_observation"], "TimeLimit.truncated", Monitor's infos[i]["episode"], get_attr / set_attr /
+infos[i]["terminal_observation"], Monitor's infos[i]["episode"], optional "TimeLimit.truncated", get_attr / set_attr /
 env_method / env_is_wrapped / seed / close).  stable-baselines3 and gym are not importable in the build image, so the
 class subclasses SB3's VecEnv only when it is present and otherwise duck-types the same methods; spaces fall back to
 small stand-ins with the attributes SB3 reads (shape, dtype, low, high, spaces).
@@ -12,6 +12,7 @@ small stand-ins with the attributes SB3 reads (shape, dtype, low, high, spaces).
 """
 import time
 from collections.abc import Sequence
+from enum import Enum
 
 import numpy as np
 
@@ -83,16 +84,51 @@ def target_direction(direction):
     return np.array([np.cos(theta), np.sin(theta)])
 
 
-STATUS_NAMES = ("RUNNING", "FAIL", "TIME_LIMIT")  # RobotEnv.Status, robot_env.py:19-22
+class Status(Enum):
+    """RobotEnv.Status (robot_env.py:19-22): same member names and values, so `info["status"].value` / `.name` work."""
+    RUNNING = 0
+    FAIL = 1
+    TIME_LIMIT = 2
+
+
+STATUS_NAMES = tuple(m.name for m in Status)
+
+
+def intrinsic_reward(old_obs, new_obs, full_observation=True):
+    """IntrinsicReward.intrinsic_reward (reward.py:57-77) for one stored transition: KL(old || new) between the 256-bin
+    histograms of the grey image (cv2.COLOR_BGR2GRAY applied to RGB-ordered data, i.e. channel 0 takes the blue weight:
+    (c0*3735 + c1*19235 + c2*9798 + 16384) >> 15) and, with the depth channel, the mean of both terms.  float32 pdfs as
+    utils.make_pdf; terms with a zero bin on either side contribute nothing (rel_entr's inf is zeroed at reward.py:67)."""
+    def pdf(img):
+        h = np.bincount(img.reshape(-1), minlength=256).astype(np.float32)
+        return h / np.float32(img.size)
+
+    def kl(p, q):
+        m = (p > 0) & (q > 0)
+        return float(np.sum(p[m] * np.log(p[m] / q[m])))
+
+    def grey(o):
+        c = o[:3].astype(np.uint32)
+        return ((c[0] * 3735 + c[1] * 19235 + c[2] * 9798 + 16384) >> 15).astype(np.uint8)
+
+    old_obs, new_obs = np.asarray(old_obs), np.asarray(new_obs)
+    r = kl(pdf(grey(old_obs)), pdf(grey(new_obs)))
+    if full_observation:
+        r = (r + kl(pdf(old_obs[3]), pdf(new_obs[3]))) / 2
+    return float(r)
 
 
 class LazyInfos(Sequence):
-    """infos of one vectorised step; infos[i] is built on demand from the packed info rows."""
+    """infos of one vectorised step; infos[i] (the 16 keys of robot_env.py:226-241 plus the VecEnv / Monitor extras) is built
+    on demand from the packed info rows.  The image-valued keys are views into the environment's pinned host buffers: they
+    stay valid until the next-but-one step() (the buffers flip every step); copy what has to live longer."""
 
-    def __init__(self, rows, dones, terminal_obs, target_dir, t_start, extra=None):
+    def __init__(self, rows, dones, terminal_obs, target_dir, t_start, extra=None, obs=None, prev_obs=None, episode_rewards=None,
+                 finished_rewards=None, truncation_key=False):
         self._rows, self._dones, self._tobs, self._dir, self._t0 = rows, dones, terminal_obs, target_dir, t_start
         self._cache = {}
         self._extra = extra or {}
+        self._obs, self._prev_obs, self._ep_rew, self._fin_rew, self._trunc = obs, prev_obs, episode_rewards, finished_rewards or {}, truncation_key
 
     def __len__(self):
         return len(self._rows)
@@ -107,26 +143,34 @@ class LazyInfos(Sequence):
         r = self._rows[i]
         I = INFO
         status = int(r[I["STATUS"]])
-        d = {"init_obj_pos": r[I["INIT_OBJ_POS"]:I["INIT_OBJ_POS"] + 3].astype(np.float64),
+        done = bool(self._dones[i])
+        tob = self._tobs.get(i) if (done and self._tobs is not None) else None
+        d = {"old_obs": None if self._prev_obs is None else self._prev_obs[i],
+             "new_obs": tob if tob is not None else (None if self._obs is None else self._obs[i]),
+             "init_obj_pos": r[I["INIT_OBJ_POS"]:I["INIT_OBJ_POS"] + 3].astype(np.float64),
              "final_obj_pos": r[I["FINAL_OBJ_POS"]:I["FINAL_OBJ_POS"] + 3].astype(np.float64),
              "target_dir": self._dir,
              "gripper_open": bool(r[I["GRIPPER_OPEN"]]),
              "controls": np.zeros(2),  # ctrl[5:7] is always zero when step() returns (robot_env.py:149,168)
              "object_grasped": int(r[I["OBJECT_GRASPED"]]),
              "episode_step": int(r[I["EPISODE_STEP"]]),
-             "status": STATUS_NAMES[status],
+             # robot_env.py:199,232: the episode's reward array, filled up to this step (the reference hands out its live array)
+             "episode_rewards": self._fin_rew[i] if i in self._fin_rew else (None if self._ep_rew is None else self._ep_rew[i]),
+             "status": Status(status),
              "gripper_position": r[I["GRIPPER_POS"]:I["GRIPPER_POS"] + 3].astype(np.float64),
              "object_position": r[I["FINAL_OBJ_POS"]:I["FINAL_OBJ_POS"] + 3].astype(np.float64),
              "position_reached": {"target": bool(r[I["REACHED_TARGET"]]), "initial": bool(r[I["REACHED_INITIAL"]]), "fail": bool(r[I["FAIL"]])},
              "total_distance": float(r[I["TOTAL_DISTANCE"]]),
              "line_distance": float(r[I["LINE_DISTANCE"]]),
+             # extras (not in the reference's dict)
              "substeps": int(r[I["NSUB_A"]] + r[I["NSUB_B"]] + r[I["NSUB_C"]]),
              "achieved_goal": r[I["ACHIEVED"]:I["ACHIEVED"] + 2].copy(),
              "desired_goal": r[I["DESIRED"]:I["DESIRED"] + 2].copy()}
-        if self._dones[i]:
-            d["TimeLimit.truncated"] = status == 2
-            if self._tobs is not None:
-                d["terminal_observation"] = {"observation": self._tobs[i], "achieved_goal": d["achieved_goal"], "desired_goal": d["desired_goal"]}
+        if done:
+            if self._trunc:
+                d["TimeLimit.truncated"] = status == 2
+            if tob is not None:
+                d["terminal_observation"] = {"observation": tob, "achieved_goal": d["achieved_goal"], "desired_goal": d["desired_goal"]}
             d["episode"] = {"r": float(r[I["EPISODE_RETURN"]]), "l": int(r[I["EPISODE_STEP"]]), "t": round(time.time() - self._t0, 6)}
         for k, v in self._extra.items():
             d[k] = v[i]
@@ -134,14 +178,36 @@ class LazyInfos(Sequence):
         return d
 
 
+class _HostBuffers:
+    """One set of pinned host arrays a step writes into."""
+
+    def __init__(self, pin, N, obs_shape, adim):
+        import torch
+        C, H, W = obs_shape
+        self.obs = pin((N, C, H, W), torch.uint8)
+        self.ag, self.dg = pin((N, 2), torch.float32), pin((N, 2), torch.float32)
+        self.rew, self.done = pin((N,), torch.float32), pin((N,), torch.uint8)
+        self.info = pin((N, INFO["STRIDE"]), torch.float32)
+
+
 class BatchedRobotVecEnv(_VecEnvBase):
-    """VecEnv of `num_envs` RobotEnv instances (reference simulation/environment/robot_env.py) on one GPU."""
+    """VecEnv of `num_envs` RobotEnv instances (reference simulation/environment/robot_env.py) on one GPU.
+
+    Host-side cost per step is O(1) in python: the simulator stores observations straight into PINNED host arrays while the
+    kernel runs (C-ABI grs_step_host), and step() returns VIEWS of those arrays.  Two buffer sets alternate, so what one
+    step returned stays intact during the next step (SB3 keeps `_last_obs` exactly that long) and is overwritten by the one
+    after; pass copy_outputs=True to get private copies instead (one 20 KB memcpy per environment and step).
+    """
 
     metadata = {"render.modes": ["rgb_array", "depth_array"]}
+    Status = Status
 
-    def __init__(self, config=None, num_envs=1, device=0, monitor_file=None, **overrides):
+    def __init__(self, config=None, num_envs=1, device=0, monitor_file=None, copy_outputs=False, truncation_as_timeout=False, _sim=None, **overrides):
         """monitor_file: directory or file prefix of a stable-baselines3 `monitor.csv` (train_agent.py:22 wraps the
-        environment in `Monitor(env, log_dir)`); one `r,l,t` row is appended per finished episode."""
+        environment in `Monitor(env, log_dir)`); one `r,l,t` row is appended per finished episode.
+        truncation_as_timeout: add infos[i]["TimeLimit.truncated"] when an episode ends at time_horizon.  The reference never
+        wraps RobotEnv in gym's TimeLimit (train_agent.py:17-23), so the key does not exist there and SB3 treats the time
+        horizon as a terminal state; off by default to keep the reference's training targets."""
         if config is None:
             config = make_config(**overrides)
         self.config = config
@@ -149,7 +215,11 @@ class BatchedRobotVecEnv(_VecEnvBase):
         if monitor_file is not None:
             from .sb3_io import MonitorWriter
             self._monitor = MonitorWriter(monitor_file)
-        self.sim = GripperSim(config, num_envs=num_envs, device=device, auto_reset=True)
+        # _sim: wrap an existing simulator (created with auto_reset=True) instead of building one; close() then leaves it open
+        self._own_sim = _sim is None
+        self.sim = GripperSim(config, num_envs=num_envs, device=device, auto_reset=True) if _sim is None else _sim
+        if self.sim.num_envs != int(num_envs):
+            raise ValueError("num_envs does not match the simulator")
         self.observation_space, self.action_space = make_spaces(config)
         if _VecEnvBase is not object:  # pragma: no cover
             super().__init__(num_envs, self.observation_space, self.action_space)
@@ -157,45 +227,68 @@ class BatchedRobotVecEnv(_VecEnvBase):
         self.target_direction = target_direction(config.direction)
         self._t_start = time.time()
         self._actions = None
+        self._copy, self._trunc = bool(copy_outputs), bool(truncation_as_timeout)
         import torch
-        N, (C, H, W) = self.num_envs, self.sim.obs_shape
+        N = self.num_envs
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
         self._h_act = pin((N, self.sim.action_dim), torch.float32)
-        self._h_obs = pin((N, C, H, W), torch.uint8)
-        self._h_tobs = pin((N, C, H, W), torch.uint8)
-        self._h_ag, self._h_dg = pin((N, 2), torch.float32), pin((N, 2), torch.float32)
-        self._h_rew, self._h_done = pin((N,), torch.float32), pin((N,), torch.uint8)
-        self._h_info = pin((N, INFO["STRIDE"]), torch.float32)
+        self._bufs = [_HostBuffers(pin, N, self.sim.obs_shape, self.sim.action_dim) for _ in range(2)]
+        self._cur = 0  # buffer set holding the most recent observation
+        self._h_tobs = pin((N,) + tuple(self.sim.obs_shape), torch.uint8)  # rows are written for finished episodes only
+        # robot_env.py:68,199: per-episode reward array of every environment (host mirror, one scatter per step)
+        self._ep_rewards = np.zeros((N, int(config.time_horizon)), np.float64)
+        self._ep_pos = np.zeros(N, np.int64)
+        self._rows = np.arange(N)
 
     # ------------------------------------------------------------------ VecEnv protocol
     def reset(self):
-        self.sim.reset_host(self._h_obs, self._h_ag, self._h_dg)
-        return self._obs_dict()
+        b = self._bufs[self._cur]
+        self.sim.reset_host(b.obs, b.ag, b.dg)
+        self._ep_rewards[...] = 0
+        self._ep_pos[...] = 0
+        return self._obs_dict(b)
 
     def step_async(self, actions):
         a = np.asarray(actions, dtype=np.float32)
         if a.shape != self._h_act.shape:
             raise ValueError("actions must have shape %s, got %s" % (self._h_act.shape, a.shape))
-        self._h_act[...] = np.clip(a, -1.0, 1.0)
+        np.clip(a, -1.0, 1.0, out=self._h_act)
         self._actions = self._h_act
 
     def step_wait(self):
         if self._actions is None:
             raise RuntimeError("step_wait() called without step_async()")
-        self.sim.step_host(self._actions, self._h_obs, self._h_ag, self._h_dg, self._h_rew, self._h_done, self._h_info, self._h_tobs)
+        prev = self._bufs[self._cur]
+        self._cur ^= 1
+        b = self._bufs[self._cur]
+        self.sim.step_host(self._actions, b.obs, b.ag, b.dg, b.rew, b.done, b.info, self._h_tobs)
         self._actions = None
-        dones = self._h_done.astype(bool)
-        infos = LazyInfos(self._h_info.copy(), dones, self._h_tobs.copy() if dones.any() else None, self.target_direction, self._t_start)
-        if self._monitor is not None and dones.any():
+        dones = b.done.view(np.bool_)
+        # episode reward arrays (robot_env.py:199): reward of this step at the episode step it was taken at
+        T = self._ep_rewards.shape[1]
+        self._ep_rewards[self._rows, np.minimum(self._ep_pos, T - 1)] = b.rew
+        self._ep_pos += 1
+        tobs, finished = None, None
+        if dones.any():
+            idx = np.flatnonzero(dones)
+            tobs = {int(i): self._h_tobs[i].copy() for i in idx}  # the shared terminal buffer is rewritten by later episodes
+            finished = {int(i): self._ep_rewards[i].copy() for i in idx}
+            self._ep_rewards[idx] = 0
+            self._ep_pos[idx] = 0
+        infos = LazyInfos(b.info.copy() if self._copy else b.info, dones.copy() if self._copy else dones, tobs, self.target_direction, self._t_start,
+                          obs=b.obs, prev_obs=prev.obs, episode_rewards=self._ep_rewards, finished_rewards=finished, truncation_key=self._trunc)
+        if self._monitor is not None and tobs is not None:
             self._monitor.write_step(dones, infos)
-        return self._obs_dict(), self._h_rew.copy(), dones, infos
+        return self._obs_dict(b), (b.rew.copy() if self._copy else b.rew), (dones.copy() if self._copy else dones), infos
 
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
 
-    def _obs_dict(self):
-        return {"observation": self._h_obs.copy(), "achieved_goal": self._h_ag.copy(), "desired_goal": self._h_dg.copy()}
+    def _obs_dict(self, b):
+        if self._copy:
+            return {"observation": b.obs.copy(), "achieved_goal": b.ag.copy(), "desired_goal": b.dg.copy()}
+        return {"observation": b.obs, "achieved_goal": b.ag, "desired_goal": b.dg}
 
     # zero-copy device path (rollouts that keep the policy on the GPU): tensors alias the simulator's buffers
     def step_tensors(self, actions):
@@ -203,10 +296,16 @@ class BatchedRobotVecEnv(_VecEnvBase):
         s = self.sim
         return {"observation": s.obs, "achieved_goal": s.achieved_goal, "desired_goal": s.desired_goal}, s.reward, s.done, s.info
 
+    @property
+    def last_info_rows(self):
+        """Packed info records [N, INFO.STRIDE] of the most recent step (a view of the pinned array; layout in _native.INFO)."""
+        return self._bufs[self._cur].info
+
     def close(self):
         if self._monitor is not None:
             self._monitor.close()
-        self.sim.close()
+        if self._own_sim:
+            self.sim.close()
 
     def seed(self, seed=None):
         # the reference creates np_random but never consumes it (robot_env.py:28,46): resets are deterministic
@@ -225,7 +324,7 @@ class BatchedRobotVecEnv(_VecEnvBase):
             if attr_name == "gripper_open":
                 return [bool(v) for v in vals]
             if attr_name == "status":
-                return [STATUS_NAMES[int(v)] for v in vals]
+                return [Status(int(v)) for v in vals]
             return [int(v) for v in vals]
         if hasattr(self, attr_name):
             return [getattr(self, attr_name)] * n
@@ -269,8 +368,9 @@ class BatchedRobotVecEnv(_VecEnvBase):
 
     # ------------------------------------------------------------------ HER support
     def compute_reward(self, achieved_goal, desired_goal, info):
-        """RobotEnv.compute_reward (robot_env.py:243-273) for stored transitions: progress reward from the recorded
-        object positions (+ the HER goal term).  `info` may be one dict or a sequence/array of dicts."""
+        """RobotEnv.compute_reward (robot_env.py:243-273) for stored transitions: progress reward from the recorded object
+        positions, + the intrinsic KL term between info["old_obs"] and info["new_obs"] when config.im_reward
+        (reward.py:45-77), + the HER goal term when config.her_buffer.  `info` may be one dict or a sequence/array of dicts."""
         infos = [info] if isinstance(info, dict) else list(info)
         ag = np.atleast_2d(np.asarray(achieved_goal, dtype=np.float32))
         dg = np.atleast_2d(np.asarray(desired_goal, dtype=np.float32))
@@ -289,6 +389,10 @@ class BatchedRobotVecEnv(_VecEnvBase):
                     if fp[2] > 0:
                         r *= 1.5
             out[k] = r * 30
+            if self.config.im_reward:
+                if inf.get("old_obs") is None or inf.get("new_obs") is None:
+                    raise KeyError("compute_reward with im_reward needs info['old_obs'] and info['new_obs'] (robot_env.py:250-251)")
+                out[k] += intrinsic_reward(inf["old_obs"], inf["new_obs"], bool(self.config.full_observation))
             if self.config.her_buffer:
                 out[k] += 1.0 / np.exp(np.linalg.norm(dg[min(k, len(dg) - 1)] - ag[min(k, len(ag) - 1)]))
         return out if not isinstance(info, dict) else float(out[0])

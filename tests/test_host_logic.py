@@ -24,19 +24,39 @@ def _rows(n):
 
 
 def test_lazy_infos_follow_the_reference_keys_and_sb3_conventions():
+    from mujoco_rl_manipulate_unknown_objects_b200.vec_env import Status, intrinsic_reward
     rows, dones = _rows(3), np.array([False, True, True])
-    tobs = np.arange(3 * 5 * 4 * 4, dtype=np.uint8).reshape(3, 5, 4, 4)
-    infos = LazyInfos(rows, dones, tobs, np.array([1, 0]), t_start=0.0)
+    obs = np.arange(3 * 5 * 4 * 4, dtype=np.uint8).reshape(3, 5, 4, 4)
+    prev = obs[::-1].copy()
+    tobs = {1: obs[1] + 7, 2: obs[2] + 9}            # terminal observations exist for finished episodes only
+    ep = np.arange(3 * 6, dtype=np.float64).reshape(3, 6)
+    fin = {1: np.ones(6), 2: np.full(6, 2.0)}
+    infos = LazyInfos(rows, dones, tobs, np.array([1, 0]), t_start=0.0, obs=obs, prev_obs=prev, episode_rewards=ep, finished_rewards=fin,
+                      truncation_key=True)
     assert len(infos) == 3 and len(infos[:]) == 3 and infos[-1] is infos[2]
     a = infos[0]
-    assert {"init_obj_pos", "final_obj_pos", "target_dir", "gripper_open", "controls", "object_grasped", "episode_step", "status",
-            "gripper_position", "object_position", "position_reached", "total_distance", "line_distance"} <= set(a)
-    assert a["status"] == "RUNNING" and a["gripper_open"] is True and a["substeps"] == 194 and "episode" not in a and "terminal_observation" not in a
+    # robot_env.py:226-241: the sixteen keys, in the reference's order
+    assert list(a)[:16] == ["old_obs", "new_obs", "init_obj_pos", "final_obj_pos", "target_dir", "gripper_open", "controls", "object_grasped",
+                            "episode_step", "episode_rewards", "status", "gripper_position", "object_position", "position_reached",
+                            "total_distance", "line_distance"]
+    assert a["status"] is Status.RUNNING and a["status"].value == 0 and a["gripper_open"] is True and a["substeps"] == 194
+    assert "episode" not in a and "terminal_observation" not in a and "TimeLimit.truncated" not in a
+    np.testing.assert_array_equal(a["old_obs"], prev[0]); np.testing.assert_array_equal(a["new_obs"], obs[0])
+    np.testing.assert_array_equal(a["episode_rewards"], ep[0])
     np.testing.assert_array_equal(a["controls"], np.zeros(2))  # robot_env.py:149,168: ctrl[5:7] is zero when step() returns
     b, c = infos[1], infos[2]
-    assert b["status"] == "TIME_LIMIT" and b["TimeLimit.truncated"] is True and c["status"] == "FAIL" and c["TimeLimit.truncated"] is False
+    assert b["status"] is Status.TIME_LIMIT and b["TimeLimit.truncated"] is True and c["status"] is Status.FAIL and c["TimeLimit.truncated"] is False
     assert b["episode"]["l"] == 400 and abs(b["episode"]["r"] - 1.5) < 1e-6 and b["episode"]["t"] > 0
     np.testing.assert_array_equal(b["terminal_observation"]["observation"], tobs[1])
+    np.testing.assert_array_equal(b["new_obs"], tobs[1])          # the finished episode's last image, not the next episode's first
+    np.testing.assert_array_equal(b["episode_rewards"], fin[1])
+    # default: no TimeLimit.truncated key (the reference has no TimeLimit wrapper, train_agent.py:17-23)
+    assert "TimeLimit.truncated" not in LazyInfos(rows, dones, tobs, np.array([1, 0]), t_start=0.0)[1]
+    # the host-side intrinsic term against the reference's own IntrinsicReward outputs (tests/golden/unit_vectors.npz)
+    u = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "unit_vectors.npz"))
+    for i in range(len(u["ir_full"])):
+        assert abs(intrinsic_reward(u["ir_a"][i], u["ir_b"][i], True) - u["ir_full"][i]) < 1e-6
+        assert abs(intrinsic_reward(u["ir_a"][i][[0, 1, 2, 4]], u["ir_b"][i][[0, 1, 2, 4]], False) - u["ir_rgb"][i]) < 1e-6
     assert STATUS_NAMES == ("RUNNING", "FAIL", "TIME_LIMIT")  # RobotEnv.Status, robot_env.py:19-22
 
 
