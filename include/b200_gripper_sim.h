@@ -177,6 +177,24 @@ GRS_API int32_t grp_shape(const grp_policy* p, int32_t* out10);
 GRS_API uint64_t grp_launch_count(const grp_policy* p);
 GRS_API void* grp_stream(const grp_policy* p);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * On-device PPO loop: what replaces the host-side replay buffer + optimiser round trip of
+ * train_agent.py:82-88 for rollouts whose storage stays in HBM.  Device pointers only; stream = cudaStream_t as void*
+ * (NULL = the legacy default stream).
+ *
+ * grl_gae: generalised advantage estimation over the rollout storage.  rewards f32[T][N], dones u8[T][N] (1 = the episode
+ * ended with this transition), values f32[T+1][N] (the last row bootstraps) -> adv f32[T][N], ret = adv + values[:T];
+ * moments_dev (may be NULL): double[2] receiving sum(adv) and sum(adv^2) for the advantage normalisation.
+ *
+ * grl_adam_step: Adam (torch.optim.Adam semantics, eps outside the square root) over ONE flat parameter bucket; grads are
+ * multiplied by grad_scale first (1/world after a SUM all-reduce of the same buffer).  step counts from 1.  Buffers must be
+ * 16-byte aligned. */
+GRS_API const char* grl_last_error(void);
+GRS_API int32_t grl_gae(const float* rewards_dev, const uint8_t* dones_dev, const float* values_dev, float* adv_dev, float* ret_dev, double* moments_dev,
+                        int32_t T, int32_t N, float gamma, float lam, void* stream);
+GRS_API int32_t grl_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t count, int32_t step,
+                              float lr, float beta1, float beta2, float eps, float grad_scale, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

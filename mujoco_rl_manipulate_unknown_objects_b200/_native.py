@@ -37,11 +37,14 @@ SYMBOLS = ["grs_last_error", "grs_default_config", "grs_create", "grs_destroy", 
 SYMBOLS += ["grp_last_error", "grp_create", "grp_destroy", "grp_num_params", "grp_set_params", "grp_get_params", "grp_forward",
             "grp_buffer", "grp_shape", "grp_launch_count", "grp_stream"]
 
+SYMBOLS += ["grl_last_error", "grl_gae", "grl_adam_step"]
+
 _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    # GRS_LIB: an alternative build of the library (development A/B runs of kernel variants); default = the in-tree build
+    return os.environ.get("GRS_LIB") or _build.LIB
 
 
 def load():
@@ -104,6 +107,9 @@ def load():
     L.grp_launch_count.argtypes = [vp]
     L.grp_stream.restype = vp
     L.grp_stream.argtypes = [vp]
+    L.grl_last_error.restype = C.c_char_p
+    L.grl_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, vp]
+    L.grl_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     _lib = L
     return L
 

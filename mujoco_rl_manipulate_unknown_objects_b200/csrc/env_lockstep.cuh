@@ -228,7 +228,16 @@ __global__ void k_order_envs(SimBuffers s, const float* __restrict__ actions, in
   s.done_list[env] = -1;
 }
 
-constexpr int LS_MAX_THREADS = 512;  // 16 warps: leaves 128 registers per thread (2 blocks of 8 warps per SM in production)
+// Launch bounds (320 threads, 2 blocks per SM) cap the kernel at 96 registers.  Measured in the steady state of the bench
+// workload (profiles/r2e_warps_regs_ab.log, r2f_regs.log): 113-120 registers (bounds 512, 1) 18.2 M substeps/s, 96 registers
+// 19.1 M, 80 registers 18.4 M, 72 registers 17.4 M, 64 registers 17.2 M; the stack frame grows by only 40 bytes at 96.
+#ifndef GRS_LS_THREADS
+#define GRS_LS_THREADS 320
+#endif
+#ifndef GRS_LS_MINBLOCKS
+#define GRS_LS_MINBLOCKS 2
+#endif
+constexpr int LS_MAX_THREADS = GRS_LS_THREADS;
 
 // TIMING = true: per-stage clock64 bookkeeping (sum over warps vs. per-round block maximum) into s.debug — a development
 // aid behind GRS_STEP_TIMING=1 that quantifies what the block barriers cost; the production instantiation carries none of it.
@@ -241,7 +250,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // FUSED = true: a block whose physics work is exhausted goes on to build observations (render_phase) instead of exiting, so
 // the rasteriser fills the SMs that idle while the longest substep chains finish.  Needs blockDim.x == RTHREADS.
 template <bool TIMING, bool FUSED>
-__global__ void __launch_bounds__(LS_MAX_THREADS, 1) k_env_step_ls(SimBuffers s, EnvCfg c, const float* __restrict__ actions, int adim, RenderScene sc, ObsArgs oa) {
+__global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_ls(SimBuffers s, EnvCfg c, const float* __restrict__ actions, int adim, RenderScene sc, ObsArgs oa) {
   unsigned smid = 0;
   if (FUSED && threadIdx.x == 0) {
     atomicMin(s.tstamp, global_ns());

@@ -191,6 +191,95 @@ def build_actor_critic(channels=5, action_dim=6, n_flatten=1024):
     return ActorCritic()
 
 
+def gae_device(rewards, dones, values, gamma, lam, stream=None, want_moments=True):
+    """GAE + returns by the library kernel grl_gae (csrc/train_kernels.cu).  rewards f32[T,N], dones u8[T,N], values f32[T+1,N]
+    CUDA tensors -> (adv f32[T,N], ret f32[T,N], moments f64[2] = sum(adv), sum(adv^2))."""
+    import ctypes as C
+    import torch
+    from . import _native
+    T, N = rewards.shape
+    assert rewards.is_cuda and rewards.dtype == torch.float32 and rewards.is_contiguous()
+    assert dones.dtype == torch.uint8 and dones.is_contiguous() and tuple(dones.shape) == (T, N)
+    assert values.dtype == torch.float32 and values.is_contiguous() and tuple(values.shape) == (T + 1, N)
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    mom = torch.zeros(2, dtype=torch.float64, device=rewards.device) if want_moments else None
+    st = stream if stream is not None else (torch.cuda.current_stream(rewards.device).cuda_stream or 1)
+    L = _native.load()
+    rc = L.grl_gae(C.c_void_p(rewards.data_ptr()), C.c_void_p(dones.data_ptr()), C.c_void_p(values.data_ptr()), C.c_void_p(adv.data_ptr()),
+                   C.c_void_p(ret.data_ptr()), C.c_void_p(mom.data_ptr()) if mom is not None else None, T, N, float(gamma), float(lam), C.c_void_p(st))
+    if rc != 0:
+        raise RuntimeError(L.grl_last_error().decode())
+    return adv, ret, mom
+
+
+class FlatAdam:
+    """Adam over ONE flat fp32 bucket.  The module's parameters and gradients are re-pointed at views of two flat CUDA arrays, so
+    that (1) autograd accumulates straight into the bucket NCCL all-reduces — no concatenate before, no scatter after — and
+    (2) the optimiser step is one fused kernel (grl_adam_step, csrc/train_kernels.cu) that also applies the 1/world averaging."""
+
+    def __init__(self, module, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        import torch
+        params = [p for p in module.parameters() if p.requires_grad]
+        dev = params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]  # every view starts 16-byte aligned
+        total = sum(sizes)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        o = 0
+        for p, n in zip(params, sizes):
+            self.flat[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + p.numel()].view_as(p.data)
+            p.grad = self.grad[o:o + p.numel()].view_as(p.data)
+            o += n
+        self.params, self.count, self.step_count = params, total, 0
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.allreduce_ms = []  # device time of every gradient all-reduce (CUDA events on the launching stream)
+
+    def zero_grad(self):
+        self.grad.zero_()  # in place: the parameters keep their gradient views
+
+    def all_reduce(self):
+        """SUM all-reduce of the gradient bucket (one collective per optimiser step).  Returns the world size."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return 1
+        if self.grad.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+            e1.record()
+            self._pending = getattr(self, "_pending", []) + [(e0, e1)]
+        else:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+        return dist.get_world_size()
+
+    def harvest_timings(self):
+        import torch
+        if getattr(self, "_pending", None):
+            torch.cuda.synchronize(self.grad.device)
+            self.allreduce_ms += [a.elapsed_time(b) for a, b in self._pending]
+            self._pending = []
+        return self.allreduce_ms
+
+    def step(self, world=1):
+        import ctypes as C
+        import torch
+        from . import _native
+        for p in self.params:  # autograd must have accumulated in place
+            assert p.grad is not None and p.grad.data_ptr() >= self.grad.data_ptr() and p.grad.data_ptr() < self.grad.data_ptr() + 4 * self.count, \
+                "a parameter's gradient left the flat bucket (zero_grad(set_to_none=True) was called?)"
+        self.step_count += 1
+        L = _native.load()
+        st = torch.cuda.current_stream(self.flat.device).cuda_stream or 1
+        rc = L.grl_adam_step(C.c_void_p(self.flat.data_ptr()), C.c_void_p(self.grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
+                             C.c_void_p(self.exp_avg_sq.data_ptr()), self.count, self.step_count, float(self.lr), float(self.betas[0]), float(self.betas[1]),
+                             float(self.eps), 1.0 / float(world), float(self.weight_decay), C.c_void_p(st))
+        if rc != 0:
+            raise RuntimeError(L.grl_last_error().decode())
+
+
 class PPOLearner:
     """Clipped-surrogate PPO on trajectories collected by RolloutWorker (squashed-Gaussian policy; log-probabilities are taken
     on the pre-tanh sample, the tanh Jacobian cancels in the ratio).  Gradients are averaged over ranks in one flat bucket."""
@@ -201,7 +290,7 @@ class PPOLearner:
         torch.manual_seed(seed)  # identical initial weights on every rank
         c = worker.sim.obs_shape[0]
         self.net = build_actor_critic(c, worker.sim.action_dim, worker.policy.n_flatten).to(worker.device)
-        self.opt = torch.optim.Adam(self.net.parameters(), lr=lr)
+        self.opt = FlatAdam(self.net, lr=lr)  # flat parameter / gradient buckets + fused Adam kernel
         self.gamma, self.lam, self.clip, self.vf_coef, self.minibatch = gamma, lam, clip, vf_coef, minibatch
         self.sync_policy()
 
@@ -213,18 +302,15 @@ class PPOLearner:
         t = self.t
         T, N = storage["rewards"].shape
         with t.no_grad():
-            values = t.stack([self._values(storage["obs"][k]) for k in range(T)] + [self._values(last_obs)])
-            adv = t.zeros((T, N), device=values.device)
-            last = t.zeros(N, device=values.device)
-            for k in reversed(range(T)):
-                nd = 1.0 - storage["dones"][k].float()
-                delta = storage["rewards"][k] + self.gamma * values[k + 1] * nd - values[k]
-                last = delta + self.gamma * self.lam * nd * last
-                adv[k] = last
-            ret = adv + values[:T]
+            values = t.stack([self._values(storage["obs"][k]) for k in range(T)] + [self._values(last_obs)]).contiguous()
+            # GAE + returns + the advantage moments in one kernel over the rollout storage (csrc/train_kernels.cu : k_gae)
+            adv, ret, mom = gae_device(storage["rewards"], storage["dones"], values, self.gamma, self.lam)
             pre = storage["mu"] + t.exp(storage["log_std"]) * storage["noise"]
             logp_old = self._logp(storage["mu"], storage["log_std"], pre)
-            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+            cnt = float(T * N)
+            mean = mom[0] / cnt
+            std = t.sqrt(t.clamp(mom[1] - cnt * mean * mean, min=0.0) / max(cnt - 1.0, 1.0))  # unbiased, as torch.std
+            adv = ((adv - mean.float()) / (std.float() + 1e-8))
         obs = storage["obs"].reshape((T * N,) + tuple(storage["obs"].shape[2:]))
         pre, logp_old, adv, ret = pre.reshape(T * N, -1), logp_old.reshape(-1), adv.reshape(-1), ret.reshape(-1)
         losses = []
@@ -237,10 +323,10 @@ class PPOLearner:
                 pg = -t.min(ratio * adv[idx], t.clamp(ratio, 1 - self.clip, 1 + self.clip) * adv[idx]).mean()
                 vf = ((v - ret[idx]) ** 2).mean()
                 loss = pg + self.vf_coef * vf
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                allreduce_flat_([p.grad for p in self.net.parameters() if p.grad is not None])
-                self.opt.step()
+                self.opt.zero_grad()
+                loss.backward()                      # accumulates into the flat gradient bucket
+                world = self.opt.all_reduce()        # ONE collective on that bucket (NCCL SUM)
+                self.opt.step(world)                 # fused Adam, 1/world folded in
                 losses.append(float(loss.detach()))
         self.sync_policy()
         return float(np.mean(losses)) if losses else 0.0

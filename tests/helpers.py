@@ -19,5 +19,12 @@ def oracle_model(cm):
     return engine.Model(engine.model_dict_from_export(cm))
 
 
+def oracle_model_independent(scene):
+    """Oracle engine model built by the ORACLE's own compiler (oracle/mjcf.py) from the scene file — nothing of the product."""
+    from oracle import engine, mjcf
+    name = scene if scene.endswith(".xml") else (scene + ".xml" if scene == "gripper_two_fingers" else scene + "_env.xml")
+    return engine.Model(mjcf.compile_mjcf(os.path.join(XMLS, name)))
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)

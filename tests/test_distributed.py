@@ -77,6 +77,58 @@ def test_world2_gloo_sharding_stats_and_gradient_bucket():
     assert u0 != u1  # per-rank seeds differ
 
 
+def _bucket_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from torch import nn
+    from mujoco_rl_manipulate_unknown_objects_b200.rollout import FlatAdam
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(5, 7), nn.Tanh(), nn.Linear(7, 2))
+    opt = FlatAdam(net, lr=1e-3)
+    ptrs = [p.grad.data_ptr() for p in net.parameters()]
+    x = torch.full((4, 5), float(rank + 1))
+    opt.zero_grad()
+    net(x).sum().backward()
+    local = opt.grad.clone()
+    assert [p.grad.data_ptr() for p in net.parameters()] == ptrs       # autograd accumulated into the bucket views
+    w = opt.all_reduce()                                               # ONE collective on the flat bucket, no cat / scatter
+    q.put((rank, w, local.numpy().copy(), opt.grad.numpy().copy(), [p.grad.detach().numpy().copy() for p in net.parameters()]))
+    try:
+        opt.step(w)
+        q.put((rank, "stepped"))
+    except Exception as e:  # noqa: BLE001 - the fused Adam kernel is CUDA only: no CPU fallback
+        q.put((rank, "raised"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_flat_gradient_bucket_of_the_fused_optimiser():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2 * world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    first = sorted(g for g in got if len(g) == 5)
+    (r0, w0, l0, s0, g0), (r1, w1, l1, s1, g1) = first
+    assert w0 == w1 == 2
+    np.testing.assert_allclose(s0, l0 + l1, rtol=1e-6)
+    np.testing.assert_allclose(s1, s0, rtol=0, atol=0)
+    assert np.abs(l0 - l1).max() > 0
+    o = 0
+    for g in g0:   # the parameters' .grad are views of the reduced bucket (16-byte aligned slots)
+        np.testing.assert_array_equal(g.reshape(-1), s0[o:o + g.size])
+        o += (g.size + 3) // 4 * 4
+    assert sorted(g[1] for g in got if len(g) == 2) == ["raised", "raised"]
+
+
 def test_shard_range_properties():
     from mujoco_rl_manipulate_unknown_objects_b200.rollout import shard_range
     for total in (0, 1, 7, 4096, 4097, 32768):

@@ -18,6 +18,12 @@ CASES = [("sugar_cube", 0, {}, 3), ("sugar_cube", 45, {}, 4), ("sand_ball", 0, {
          ("gripper_two_fingers", 0, {}, 10), ("sugar_cube", 120, {}, 11)]  # 120 degrees: the `_get_direction` unit vector (robot_env.py:46-54)  # the primitive-box scene (mjc_PlaneBox + box support in MPR)
 
 
+# MEASURED (round 2, B200, 48 matched agent steps per case): steps in which the fp32 trajectory leaves the fp64 one by > 1e-4 or takes a
+# different number of substeps ("flipped by contact chaos": a grasping step is a discontinuous map).  Asserted: measured + 50 %.
+MEASURED_FLIPS = {"sugar_cube-0-default": 10, "sugar_cube-45-default": 6, "sand_ball-0-default": 2, "bread_crumb-0-default": 1, "acorn-0-default": 1,
+                  "sand_ball-45-include_roll": 5, "sugar_cube-0-her_buffer-time_horizon": 7, "gripper_two_fingers-0-default": 5, "sugar_cube-120-default": 4}
+
+
 def make(scene, direction, kw, n, auto_reset=False):
     from mujoco_rl_manipulate_unknown_objects_b200 import GripperSim, make_config
     cfg = make_config(sim_env="/xmls/%s.xml" % (scene if scene == "gripper_two_fingers" else scene + "_env"), direction=direction, **kw)
@@ -107,7 +113,8 @@ def test_agent_step_at_matched_states(scene, direction, kw, seed):
     print("\n[%s dir %d %s] %d matched agent steps, %d flipped by contact chaos, substeps %d, end-state qpos err median %.1e max %.1e, reward err median %.1e max %.1e, rewards>0: %d" % (
         scene, direction, kw, N, flipped, int(info[:, I["NSUB_A"]:I["NSUB_A"] + 3].sum()), np.median(qerrs), max(qerrs), np.median(rew_err), max(rew_err),
         sum(1 for r in ref if r["reward"] > 0)))
-    assert flipped <= N // 4
+    case = "%s-%d-%s" % (scene, direction, "-".join(kw) or "default")
+    assert flipped <= int(np.ceil(1.5 * MEASURED_FLIPS[case])), "flip count %d regressed against the measured %d" % (flipped, MEASURED_FLIPS[case])
     assert sum(1 for r in ref if r["reward"] > 0) > 0
     sim.close()
 

@@ -40,12 +40,17 @@ def _run(n, scene, steps, env=None, seed=0):
     return out
 
 
-@pytest.mark.parametrize("n,scene", [(4096, "acorn"), (8192, "sugar_cube")])
+@pytest.mark.parametrize("n,scene", [(4096, "acorn"), (8192, "sugar_cube"), (16384, "sand_ball")])  # BASELINE.json configs[1], [2], [4]
 def test_results_do_not_depend_on_scheduling(n, scene):
     import torch
-    steps = 4
+    steps = 4 if n <= 8192 else 3
     base = _run(n, scene, steps)
-    for env in (dict(GRS_FUSED_RENDER="0"), dict(GRS_STEP_WARPS="10", GRS_HULL_SMEM="0"), dict(GRS_STEP_WARPS="0")):  # 0 = sequential kernel
+    # 0 = sequential kernel; GRS_GAP_SKIP=0 evaluates every cached separating axis instead of skipping those whose separation
+    # budget is still positive (sim_kernels.cuh : collision) — the skip is exact, so not a bit may change; GRS_SLOT_ORDER=1
+    # hands the first queue entries to different blocks
+    variants = (dict(GRS_FUSED_RENDER="0"), dict(GRS_STEP_WARPS="10", GRS_HULL_SMEM="0"), dict(GRS_STEP_WARPS="0"), dict(GRS_GAP_SKIP="0"),
+                dict(GRS_SLOT_ORDER="1", GRS_NO_HOST_MIRROR="1"))
+    for env in (variants if n <= 8192 else variants[2:4]):
         other = _run(n, scene, steps, env)
         for t in range(steps):
             for k in base[t]:
@@ -54,6 +59,39 @@ def test_results_do_not_depend_on_scheduling(n, scene):
     for t in range(steps):
         for k in base[t]:
             assert torch.equal(base[t][k], again[t][k]), "run-to-run difference in %s at step %d" % (k, t)
+
+
+def test_separation_budget_skip_is_exact():
+    """sim_kernels.cuh : collision skips a convex pair while the separation measured along its cached axis, minus how far the two
+    geoms can have moved since, stays positive.  That is a proof that the axis still separates them, so the contact sets — and
+    with them every bit of the trajectory — must equal those of the kernel that evaluates the axis every substep.  40 agent
+    steps of contact-seeking actions (grippers push and squeeze the objects, fingers press against each other)."""
+    import torch
+    from mujoco_rl_manipulate_unknown_objects_b200 import GripperSim, make_config
+    n, steps = 2048, 40
+    res = []
+    for skip in ("1", "0"):
+        os.environ["GRS_GAP_SKIP"] = skip
+        try:
+            sim = GripperSim(make_config(sim_env="/xmls/bread_crumb_env.xml"), num_envs=n, auto_reset=True)
+        finally:
+            os.environ.pop("GRS_GAP_SKIP", None)
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        snap = []
+        for t in range(steps):
+            a = torch.rand((n, 6), device="cuda", generator=gen) * 2 - 1
+            a[:, 0] = 0.6 + 0.4 * a[:, 0]
+            a[:, 5] = torch.where(torch.arange(n, device="cuda") % 3 == 0, a[:, 5], -a[:, 5].abs())
+            sim.step(a)
+            if t % 8 == 7:
+                snap.append((sim.state.clone(), sim.info.clone(), sim.reward.clone(), sim.obs[::64].clone()))
+        res.append(snap)
+        sim.close()
+    from mujoco_rl_manipulate_unknown_objects_b200._native import INFO as I
+    assert float(res[0][-1][1][:, I["NCON_MAX"]].mean()) > 2.5, "the tape did not bring the batch into contact"
+    for a, b in zip(*res):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
 
 
 def test_full_batch_sanity():

@@ -7,9 +7,29 @@ Relative error of a vector x is max|x_gpu - x_ref| / max(1, max|x_ref|).
 import numpy as np
 import pytest
 
-from helpers import oracle_model
+from helpers import oracle_model, oracle_model_independent
 
 pytestmark = pytest.mark.gpu
+
+# Per-scene MEASURED statistics of test_substep_parity_at_matched_states on a B200 (96 matched states each; printed by the test,
+# `pytest -s`), with what is asserted: the measured figure + 50 % (rounded up), never the blanket N/10 / 4 % / 1e-1 of round 1.
+#   margin : states whose contact list differs only by a pair within 1e-5 of the inclusion margin (skipped, counted)
+#   dist   : contacts whose MPR distance differs by >= 2e-5 (the portal ended on another face of the Minkowski difference)
+#   v_gt   : states whose per-substep qvel relative error exceeds the north-star's 1e-4
+#   v_max  : the largest such error
+#   q_max  : the largest per-substep qpos relative error
+MEASURED = {  # round 2, B200, gpurun_out/r2e_parity.log -> profiles/r2e_parity_measured.log
+    "sugar_cube":          dict(margin=0, dist=0, v_gt=0, v_max=1.2e-05, q_max=1.1e-07),
+    "sand_ball":           dict(margin=0, dist=1, v_gt=2, v_max=3.2e-02, q_max=1.5e-04),  # one portal flip on the finger/finger pair (3, 5), one fp32-conditioning state
+    "bread_crumb":         dict(margin=0, dist=0, v_gt=0, v_max=4.6e-05, q_max=2.2e-07),
+    "acorn":               dict(margin=0, dist=0, v_gt=1, v_max=1.4e-03, q_max=5.7e-06),  # one state with a pair on the margin threshold
+    "gripper_two_fingers": dict(margin=1, dist=1, v_gt=3, v_max=1.8e-02, q_max=8.5e-05),  # portal flip (3, 5), margin threshold, Newton iteration count
+}
+
+
+def allowed(measured, floor=0):
+    """measured count + 50 %, rounded up (a count of 0 stays 0 unless a floor is given)."""
+    return max(floor, int(np.ceil(1.5 * measured)))
 
 SCENES = ["sugar_cube", "sand_ball", "bread_crumb", "acorn", "gripper_two_fingers"]  # the last one: primitive box object
 _cache = {}
@@ -19,12 +39,20 @@ def rel(a, b):
     return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(1.0, np.abs(b).max()))
 
 
-def get_sim(scene, n):
+def get_sim(scene, n, independent=False):
+    """(simulator, oracle model).  independent=False: the oracle integrates the model the PRODUCT compiler exported (same
+    principal frames and hull-vertex numbering as the kernels, so MPR ties break alike).  independent=True: the oracle's model
+    comes from its own compiler, oracle/mjcf.py — nothing of the product's model reaches the checker."""
     from mujoco_rl_manipulate_unknown_objects_b200 import GripperSim, make_config
     key = (scene, n)
     if key not in _cache:
         sim = GripperSim(make_config(sim_env="/xmls/%s.xml" % (scene if scene == "gripper_two_fingers" else scene + "_env")), num_envs=n, auto_reset=False)
         _cache[key] = (sim, oracle_model(sim))
+    if independent:
+        ikey = (scene, "independent")
+        if ikey not in _cache:
+            _cache[ikey] = oracle_model_independent(scene)
+        return _cache[key][0], _cache[ikey]
     return _cache[key]
 
 
@@ -90,7 +118,7 @@ def test_substep_parity_at_matched_states(scene):
     after = sim.get_state()
     worst = dict(qpos=0.0, qvel=0.0, M=0.0, bias=0.0, qacc=0.0)
     n_contact_states = n_pairs_equal = n_margin_skipped = n_obj_contacts = n_dist_outliers = 0
-    qerrs, verrs, flip_states = [], [], set()
+    qerrs, verrs, flip_states, causes = [], [], set(), {}
     for i in range(N):
         d = oracle_at(om, q[i], v[i], c[i], w[i])
         M_ref = d.qM.copy()
@@ -123,22 +151,78 @@ def test_substep_parity_at_matched_states(scene):
         qerrs.append(rel(after["qpos"][i], d.qpos))
         verrs.append(rel(after["qvel"][i], d.qvel))
         if verrs[-1] > 1e-4 or qerrs[-1] > 1e-4:
-            print("   substep outlier: state %d qpos %.1e qvel %.1e pairs %s iters gpu %d oracle %d ncon %d" % (
-                i, qerrs[-1], verrs[-1], ref_pairs, dbg["iters"][i], d.solver_iter, len(cons)))
+            # why: an MPR portal flip (distance outlier above), a pair on the margin threshold, a different Newton iteration count,
+            # or none of these = fp32 conditioning of a stiff contact (finger/finger: 0.02 kg bodies against solref 0.007)
+            cause = "portal flip" if i in flip_states else "margin threshold" if near else \
+                "newton iterations %d vs %d" % (dbg["iters"][i], d.solver_iter) if dbg["iters"][i] != d.solver_iter else "fp32 conditioning"
+            causes[cause.split(" ")[0]] = causes.get(cause.split(" ")[0], 0) + 1
+            print("   substep outlier: state %d qpos %.1e qvel %.1e cause: %s; pairs %s ncon %d" % (i, qerrs[-1], verrs[-1], cause, ref_pairs, len(cons)))
     qerrs, verrs = np.array(qerrs), np.array(verrs)
     print("\n[%s] %d states (%d with contacts, %d gripper/object contacts): pairs exact %d, near-margin skipped %d" % (
         scene, N, n_contact_states, n_obj_contacts, n_pairs_equal, n_margin_skipped))
     print("   per-substep rel err: qpos max %.2e  qvel max %.2e median %.2e | M %.1e bias %.1e qacc(rel to max(1,|qacc|)) %.1e" % (
         qerrs.max(), verrs.max(), np.median(verrs), worst["M"], worst["bias"], worst["qacc"]))
+    n_v_gt = int((verrs > 1e-4).sum())
+    print("   MEASURED[%r] = dict(margin=%d, dist=%d, v_gt=%d, v_max=%.1e, q_max=%.1e)   outlier causes: %s" % (
+        scene, n_margin_skipped, n_dist_outliers, n_v_gt, verrs.max(), qerrs.max(), causes))
+    ms = MEASURED[scene]
     assert n_contact_states > N // 2
-    assert n_margin_skipped <= N // 10
     assert worst["M"] < 1e-4 and worst["bias"] < 1e-4
-    assert n_dist_outliers <= 3
-    # 1e-4 per substep; a state whose MPR portal flips (counted above) may exceed it, bounded by 1e-2
+    assert n_margin_skipped <= allowed(ms["margin"]) and n_dist_outliers <= allowed(ms["dist"])
+    # north-star: 1e-4 per substep.  Exceeded only in the counted, classified states; their number and size are bounded by what
+    # was measured (+ 50 %), so a regression of the flip rate fails the test
     keep = np.array([i not in flip_states for i in range(N)])
-    assert qerrs[keep].max() <= 1e-4 and qerrs.max() <= 1e-2, "per-substep qpos relative error"
-    # stiff finger/finger contacts (pair (3, 5)) are ill-conditioned in fp32: up to 4 % of the states may exceed 1e-4 (measured: 0-3 %)
-    assert (verrs <= 1e-4).mean() >= 0.96 and verrs[keep].max() <= 1e-2 and verrs.max() <= 1e-1, "per-substep qvel relative error"
+    assert qerrs[keep].max() <= 1e-4 and qerrs.max() <= max(1e-4, 1.5 * ms["q_max"]), "per-substep qpos relative error"
+    assert n_v_gt <= allowed(ms["v_gt"]) and verrs.max() <= max(1e-4, 1.5 * ms["v_max"]), "per-substep qvel relative error"
+
+
+@pytest.mark.parametrize("scene", ["sugar_cube", "sand_ball", "bread_crumb", "acorn"])
+def test_substep_parity_against_the_independently_compiled_model(scene):
+    """The same comparison with NOTHING of the product's compiled model on the checker's side: the oracle engine integrates the
+    model built by oracle/mjcf.py (own XML / STL readers, qhull, eigen-solver: other principal-axis permutations, other hull
+    vertex numbering).  States are frame independent (joint coordinates), contact pairs are geom ids.  Differently numbered
+    hull vertices break exact support ties differently, so a few more MPR portals end on another face than in the shared-model
+    test; the bounds are again the measured ones + 50 %."""
+    N = 96
+    sim, om = get_sim(scene, N, independent=True)
+    states = visited_states(om, seed=11, nsteps=N // 3)[:N]
+    q, v, c, w = to_f32_states(states)
+    sim.reset()
+    sim.set_state(qpos=q, qvel=v, ctrl=c, warmstart=w)
+    gc = sim.contacts()
+    sim.substep(1)
+    after = sim.get_state()
+    n_equal = n_margin = 0
+    qerrs, verrs = [], []
+    for i in range(N):
+        d = oracle_at(om, q[i], v[i], c[i], w[i])
+        cons = d.contacts()
+        d.step()
+        ref_pairs = [(x["geom1"], x["geom2"]) for x in cons]
+        gpu_pairs = [tuple(p) for p in gc["geom"][i][:gc["ncon"][i]].tolist()]
+        near = any(abs(x["dist"] - 0.001) < 1e-5 for x in cons) or len(gpu_pairs) != len(ref_pairs)
+        if gpu_pairs == ref_pairs:
+            n_equal += 1
+        else:
+            assert near, "state %d: contact pairs gpu %s oracle %s dists %s" % (i, gpu_pairs, ref_pairs, [x["dist"] for x in cons])
+            n_margin += 1
+        qerrs.append(rel(after["qpos"][i], d.qpos))
+        verrs.append(rel(after["qvel"][i], d.qvel))
+    qerrs, verrs = np.array(qerrs), np.array(verrs)
+    n_v_gt = int((verrs > 1e-4).sum())
+    print("\n[%s, oracle/mjcf.py model] pairs exact %d/%d (near-margin %d); qpos max %.2e; qvel max %.2e median %.2e, > 1e-4 in %d states" % (
+        scene, n_equal, N, n_margin, qerrs.max(), verrs.max(), np.median(verrs), n_v_gt))
+    ms = MEASURED_INDEPENDENT[scene]
+    assert n_margin <= allowed(ms["margin"]) and n_v_gt <= allowed(ms["v_gt"])
+    assert qerrs.max() <= max(1e-4, 1.5 * ms["q_max"]) and verrs.max() <= max(1e-4, 1.5 * ms["v_max"]) and np.median(verrs) <= 1e-5
+
+
+MEASURED_INDEPENDENT = {  # round 2, B200: contact pairs exact in 96/96 states of every scene
+    "sugar_cube":  dict(margin=0, v_gt=2, v_max=1.52e-03, q_max=6.22e-06),
+    "sand_ball":   dict(margin=0, v_gt=3, v_max=5.00e-03, q_max=2.33e-05),
+    "bread_crumb": dict(margin=0, v_gt=0, v_max=4.55e-05, q_max=2.19e-07),
+    "acorn":       dict(margin=0, v_gt=1, v_max=3.18e-03, q_max=1.47e-05),
+}
 
 
 @pytest.mark.parametrize("scene", ["sugar_cube", "sand_ball"])
@@ -161,8 +245,11 @@ def test_hundred_substep_horizon(scene):
     errs = np.array(errs)
     print("\n[%s] 100-substep horizon: median %.2e, 90th pct %.2e, max %.2e, fraction <= 1e-2: %.3f" % (
         scene, np.median(errs), np.percentile(errs, 90), errs.max(), (errs <= 1e-2).mean()))
-    assert np.median(errs) <= 1e-3
-    assert (errs <= 1e-2).mean() >= 0.9
+    # measured (round 2, B200): sugar_cube median 4.7e-06, 93.8 % of the start states within 1e-2 (6 of 96 diverge after a contact
+    # flip); sand_ball median 2.2e-06, 97.9 % (2 of 96).  Asserted: median <= 10 x measured, diverged states <= measured + 50 %
+    med, ndiv = {"sugar_cube": (4.7e-6, 6), "sand_ball": (2.2e-6, 2)}[scene]
+    assert np.median(errs) <= 10 * med
+    assert int((errs > 1e-2).sum()) <= allowed(ndiv)
 
 
 def test_reset_state_and_free_fall():
@@ -184,3 +271,40 @@ def test_reset_state_and_free_fall():
     assert abs(s4["qpos"][0][9] - (z0 - 9.81 * 0.002 ** 2 * 10)) < 1e-6
     # determinism: identical environments stay bit-identical
     assert np.all(s4["qpos"] == s4["qpos"][0]) and np.all(s4["qvel"] == s4["qvel"][0])
+
+
+def test_contact_overflow_is_truncated_in_order_and_flagged():
+    """MAXCON = 12 contacts are kept per environment (sim_kernels.cuh; SURVEY.md §8 a-M: the geometric worst case is 27, rollouts
+    stay <= 6).  A gripper pressed flat into the floor has 17: the kernel must keep the FIRST 12 of MuJoCo's contact order (the
+    oracle keeps all of them), raise the overflow flag (info FLAGS bit 0), and carry on with finite dynamics.  Raising MAXCON to
+    16 would cost 1.8 KB of shared memory per warp — the hull vertices would no longer fit beside two 8-warp blocks per SM
+    (-2.4 % throughput, profiles/r2d_knobs.log) — and still not cover this state."""
+    import torch
+    from oracle import engine
+    from mujoco_rl_manipulate_unknown_objects_b200._native import INFO as I
+    N = 96
+    sim, om = get_sim("sugar_cube", N)
+    d = engine.Data(om)
+    d.reset()
+    d.xfrc_applied[om.body_id("ee"), 2] = 0.438 * 9.81
+    d.step(300)                      # the object settles on the floor
+    q = d.qpos.copy()
+    q[2] = -0.14                     # gripper_z: the whole gripper lies in the floor plane
+    d.qpos[:] = q
+    d.qvel[:] = 0
+    d.forward_position()
+    ref_pairs = [(c["geom1"], c["geom2"]) for c in d.contacts()]
+    K = sim._lib.grs_max_contacts()
+    assert len(ref_pairs) > K == 12, (len(ref_pairs), K)
+    sim.reset()
+    sim.set_state(qpos=np.float32(q), qvel=np.zeros(13, np.float32), ctrl=np.zeros(7, np.float32), warmstart=np.zeros(13, np.float32))
+    gc = sim.contacts()
+    assert (gc["ncon"] == K).all()
+    assert [tuple(p) for p in gc["geom"][0][:K].tolist()] == ref_pairs[:K]
+    sim.step(torch.zeros((N, 6), device=sim.device))
+    info = sim.info.cpu().numpy()
+    assert (info[:, I["FLAGS"]].astype(int) & 1).all(), "contact overflow was not flagged"
+    assert (info[:, I["NCON_MAX"]] == K).all()
+    st = sim.get_state()
+    assert np.isfinite(st["qpos"]).all() and np.isfinite(st["qvel"]).all()
+    assert st["qpos"][0][2] > -0.14   # the floor pushes the gripper back out

@@ -40,8 +40,11 @@ for it in range(a.iters):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     stats.all_reduce()
     d = stats.as_dict()
+    ar = learner.opt.harvest_timings()
+    learner.opt.allreduce_ms = []
     if rank == 0:
-        print(json.dumps({"iter": it, "n_gpus": world, "envs_per_gpu": a.envs, "rollout_steps": a.steps, "rollout_s": tm[0].item(), "update_s": tm[1].item(),
+        print(json.dumps({"iter": it, "optimizer_steps": len(ar) if world > 1 else None,
+                          "grad_allreduce_ms": {"mean": sum(ar) / len(ar), "min": min(ar), "max": max(ar), "bucket_bytes": 4 * learner.opt.count} if ar else None, "n_gpus": world, "envs_per_gpu": a.envs, "rollout_steps": a.steps, "rollout_s": tm[0].item(), "update_s": tm[1].item(),
                           "substeps_per_s": d.get("substeps", 0) / tm[0].item(), "transitions_per_s": a.envs * world * a.steps / tm[0].item(), "loss": loss, "stats": d}))
 w.close()
 if world > 1:

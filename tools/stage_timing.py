@@ -26,3 +26,11 @@ lone = d[:, 18:25].sum(0); nl = d[:, 17].sum()
 print("rounds with a single active warp in the block: %d of %d; cycles per such round %.0f (= %.1f us at 1.965 GHz); stage shares: %s" % (
     nl, d[:, 16].sum(), lone.sum() / max(nl, 1), lone.sum() / max(nl, 1) / 1965.0, ", ".join("%s %.0f%%" % (n, 100 * x / max(lone.sum(), 1)) for n, x in zip(names, lone))))
 print("total: sum of per-round maxima / sum of warp means = %.2f" % (mx.sum() / mean.sum()))
+
+# the blocks that run the longest chains (queued first: gripper-close environments, a fifth of which time out at 400 substeps)
+order = d[:, 16].argsort()[::-1]
+for name, sel in (("48 blocks with most rounds", order[:48]), ("48 blocks with fewest rounds", order[-48:])):
+    r = d[sel, 16].sum()
+    print("%s: rounds/block %.0f; kcycles per round, warp mean: %s | block max: %s | sum of max %.1f" % (
+        name, d[sel, 16].mean(), " ".join("%s %.1f" % (n, a / r / 1e3) for n, a in zip(names, d[sel, :7].sum(0))),
+        " ".join("%.1f" % (b / r / 1e3) for b in d[sel, 8:15].sum(0)), d[sel, 8:15].sum() / r / 1e3))
