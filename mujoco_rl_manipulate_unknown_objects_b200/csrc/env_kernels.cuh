@@ -271,7 +271,7 @@ __device__ __noinline__ void env_step(const DevModel& m, const EnvCfg& c, WS& w,
   __syncwarp();
   float tq_rec = lane < 5 ? w.tgt[lane] : 0.0f;
   const float scale = lane < 3 ? 1.0f / c.max_trans : 1.0f / c.max_rot;
-  int nsa = 0, nsb = 0, nsc = 0, iters = 0, nconmax = w.ncon, flags = 0;
+  int nsa = 0, nsb = 0, nsc = 0, iters = 0, nconmax = w.ncon, flags = w.overflow;  // the contact set the step starts from counts (its position stage ran at load time)
   bool reached_target = false, reached_initial = false;
   int step_limit = c.max_steps;
   // phase A: P-control towards the IK target (robot_env.py:97-110)

@@ -52,8 +52,9 @@ __device__ __noinline__ bool env_tick(const DevModel& m, const EnvCfg& c, WS& w,
         if (lane == 0) get_target_pose(m, c, w, a6);
         __syncwarp();
         t.k.tq_rec = lane < 5 ? w.tgt[lane] : 0.0f;
-        t.k.nsa = t.k.nsb = t.k.nsc = t.k.iters = t.k.flags = t.k.fail = t.k.object_grasped = 0;
+        t.k.nsa = t.k.nsb = t.k.nsc = t.k.iters = t.k.fail = t.k.object_grasped = 0;
         t.k.nconmax = w.ncon;
+        t.k.flags = w.overflow;  // the contact set the step starts from counts (its position stage ran at load time)
         t.k.reached_target = t.k.reached_initial = false;
         t.step_limit = c.max_steps;
         t.i = 0;
@@ -272,8 +273,10 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_l
   }
   __shared__ unsigned long long t_sum[8], t_max[8], t_round[8];
   __shared__ unsigned long long t_rounds, t_lone[8], t_lone_rounds;  // rounds in which exactly one warp of the block was active
+  __shared__ unsigned int t_hist[12];  // rounds with k active warps (k = 0..11)
   int prev_active = 0;
-  if (TIMING) { if (threadIdx.x < 8) { t_sum[threadIdx.x] = 0; t_max[threadIdx.x] = 0; t_round[threadIdx.x] = 0; } if (threadIdx.x == 0) { t_rounds = 0; t_lone_rounds = 0; } if (threadIdx.x < 8) t_lone[threadIdx.x] = 0; __syncthreads(); }
+  const long long t_block0 = TIMING ? clock64() : 0;
+  if (TIMING) { if (threadIdx.x < 8) { t_sum[threadIdx.x] = 0; t_max[threadIdx.x] = 0; t_round[threadIdx.x] = 0; } if (threadIdx.x == 0) { t_rounds = 0; t_lone_rounds = 0; } if (threadIdx.x < 8) t_lone[threadIdx.x] = 0; if (threadIdx.x < 12) t_hist[threadIdx.x] = 0; __syncthreads(); }
   long long t0 = 0;
 #define LS_T0() if (TIMING) t0 = clock64();
 #define LS_T1(p) if (TIMING) { unsigned long long d_ = (unsigned long long)(clock64() - t0); if (lane == 0) { atomicAdd(&t_sum[p], d_); atomicMax(&t_round[p], d_); } }
@@ -315,6 +318,7 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_l
     if (TIMING && threadIdx.x == 0) {
       for (int p = 0; p < 8; p++) { t_max[p] += t_round[p]; if (prev_active == 1) t_lone[p] += t_round[p]; t_round[p] = 0; }
       t_rounds++;
+      t_hist[min(n_active, 11)]++;
       if (prev_active == 1) t_lone_rounds++;
     }
     prev_active = n_active;
@@ -368,6 +372,10 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_l
     }
     if (threadIdx.x == 0) { s.debug[(size_t)blockIdx.x * 32 + 16] = (float)t_rounds; s.debug[(size_t)blockIdx.x * 32 + 17] = (float)t_lone_rounds; }
     if (threadIdx.x < 8) s.debug[(size_t)blockIdx.x * 32 + 18 + threadIdx.x] = (float)t_lone[threadIdx.x];
+    // block-level record (second half of the debug buffer): physics-phase duration in cycles, then rounds with k active warps
+    float* bd = s.debug + (size_t)gridDim.x * 32 + (size_t)blockIdx.x * 16;
+    if (threadIdx.x == 0) bd[0] = (float)(clock64() - t_block0);
+    if (threadIdx.x >= 1 && threadIdx.x < 13) bd[threadIdx.x] = (float)t_hist[threadIdx.x - 1];
   }
 #undef LS_T0
 #undef LS_T1

@@ -10,7 +10,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -33,6 +35,21 @@ static int fail(const std::string& msg) { g_err = msg; return 1; }
     cudaError_t e_ = (call);                                                                         \
     if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
+
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (kernel, device) pair, not to a simulator: several simulators of one
+// process (different scenes -> different hull sizes) share it, so it is only ever raised — lowering it would make the launches of
+// an older, larger simulator fail with "invalid argument".
+static void raise_dyn_smem(const void* func, size_t bytes, int device) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> cur;
+  std::lock_guard<std::mutex> g(mu);
+  size_t& c = cur[std::make_pair(func, device)];
+  if (bytes > c) {
+    CU(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    c = bytes;
+  }
+}
 
 struct grs_sim {
   HostModel hm;
@@ -182,11 +199,11 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     e.pos_tol = cfg.pos_tolerance; e.grasp_tol = cfg.grasp_tolerance; e.max_trans = cfg.max_translation; e.max_rot = cfg.max_rotation;
     // launch geometry: persistent blocks, as many as fit (one WS per warp in shared memory)
     s->smem = smem_bytes();
-    CU(cudaFuncSetAttribute(k_env_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
-    CU(cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
-    CU(cudaFuncSetAttribute(k_contacts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
-    CU(cudaFuncSetAttribute(k_debug_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
-    CU(cudaFuncSetAttribute(k_make_reset_record, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
+    raise_dyn_smem((const void*)k_env_step, s->smem, device);
+    raise_dyn_smem((const void*)k_substep, s->smem, device);
+    raise_dyn_smem((const void*)k_contacts, s->smem, device);
+    raise_dyn_smem((const void*)k_debug_step, s->smem, device);
+    raise_dyn_smem((const void*)k_make_reset_record, s->smem, device);
     int per_sm = 0, nsm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_step, WARPS_PER_BLOCK * 32, s->smem));
     CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
@@ -206,9 +223,9 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
       // the observation phase needs RTHREADS-wide blocks and the observation tile in the block's shared memory
       s->fused_render = !s->ls_timing && s->ls_warps * 32 == RTHREADS && s->ls_smem >= render_phase_smem_bytes() && cfg.width <= TILE && cfg.height <= TILE;
       if (const char* e = getenv("GRS_FUSED_RENDER")) s->fused_render = s->fused_render && atoi(e) != 0;
-      CU(cudaFuncSetAttribute(k_env_step_ls<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
-      CU(cudaFuncSetAttribute(k_env_step_ls<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
-      CU(cudaFuncSetAttribute(k_env_step_ls<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->ls_smem));
+      raise_dyn_smem((const void*)k_env_step_ls<false, false>, s->ls_smem, device);
+      raise_dyn_smem((const void*)k_env_step_ls<false, true>, s->ls_smem, device);
+      raise_dyn_smem((const void*)k_env_step_ls<true, false>, s->ls_smem, device);
       int ls_per_sm = 0;
       if (s->fused_render) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, k_env_step_ls<false, true>, s->ls_warps * 32, s->ls_smem));
       else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, k_env_step_ls<false, false>, s->ls_warps * 32, s->ls_smem));

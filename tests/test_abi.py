@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "b200_gripper_sim.h")
 def _declared():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return re.findall(r"GRS_API\s+[\w\s\*]+?\b(gr[sp]_\w+)\s*\(", src)
+    return re.findall(r"GRS_API\s+[\w\s\*]+?\b(gr[spl]_\w+)\s*\(", src)
 
 
 def test_library_exports_every_declared_symbol():
