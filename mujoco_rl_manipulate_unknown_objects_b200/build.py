@@ -13,8 +13,13 @@ LIB = os.path.join(HERE, "libgripper_sim_b200.so")
 SOURCES = ["gripper_sim.cu", "policy_kernels.cu", "train_kernels.cu", "mjcf_compiler.cpp", "dev_model.cpp"]
 HEADERS = ["model.h", "sim_kernels.cuh", "env_kernels.cuh", "env_lockstep.cuh", "render_kernels.cuh",
            os.path.join("..", "..", "include", "b200_gripper_sim.h")]
+# -prec-div=false / -prec-sqrt=false / -ftz=true: divisions and square roots are the hardware's 2-ulp approximations and
+# denormals flush to zero.  The physics kernel divides and normalises on every dependent chain (quaternions, contact frames,
+# Cholesky pivots, the MPR portal), and the IEEE-exact sequences (~8 instructions + a slow path each) were 12 % of the step
+# (profiles/r2k_flags.log: 18.9 -> 21.2 M substeps/s); every parity test passes unchanged with them.  NOT -use_fast_math: its
+# sin/cos/pow intrinsics change trajectories beyond the parity bounds (8 tests fail).
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-Xcompiler", "-fvisibility=hidden", "-shared", "-diag-suppress", "550"]
+              "-Xcompiler", "-fvisibility=hidden", "-shared", "-diag-suppress", "550,177", "-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
 
 
 def _nvcc():

@@ -381,7 +381,7 @@ struct SimBuffers {
   const DevModel* model;
   int n;
   int order_ncon;  // longest-first order: previous-step contact count from which an environment counts as contact-heavy
-  int slot_order;  // lock-step kernel: 0 = a block's warps take consecutive queue entries, 1 = consecutive entries go to consecutive BLOCKS (long chains spread thin)
+  int slot_order;  // lock-step kernel, first environment of a warp: 0 = consecutive queue entries per block, 1 = consecutive entries to consecutive blocks, 2 = balanced (static_slot, env_lockstep.cuh)
   int ls_mask;  // lock-step kernel: which stage boundaries carry a block barrier (bit 0 smooth | 1 constraint | 2 solve | 3 euler+kin | 4 crb)
 };
 constexpr int DEBUG_STRIDE = 2048;

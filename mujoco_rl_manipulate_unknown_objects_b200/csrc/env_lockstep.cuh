@@ -229,6 +229,32 @@ __global__ void k_order_envs(SimBuffers s, const float* __restrict__ actions, in
   s.done_list[env] = -1;
 }
 
+// First environment of a warp (static slot in the longest-first queue).
+//   slot_order 0: a block's warps take consecutive queue entries.  The first blocks then hold eight gripper-closing environments each
+//                 (three quarters of which run into the 400-substep timeout): ~485 full rounds, while the average block has ~330
+//                 rounds of work and finishes a third earlier (profiles/r2h_stage_timing_step150.log).
+//   slot_order 1: consecutive entries go to consecutive blocks (long chains spread thin, but every block mixes contact-heavy and
+//                 contact-free environments, and a lock-step round costs what its slowest warp costs).
+//   slot_order 2: balanced.  The gripper-closing class (chain-length class 0) is dealt out in equal runs, n0 / grid per block, the
+//                 rest of the static entries fill the block's other warps, also as one run: every block carries the same share of
+//                 long chains and both of its runs are contiguous in the contact-count order (homogeneous rounds).  Once the short
+//                 environments and the shared queue are exhausted, a block is left with its few long chains, which then run at
+//                 the latency of a nearly empty SM instead of that of a full one.
+__device__ __forceinline__ int static_slot(const SimBuffers& s, int nstatic) {
+  const int W = blockDim.x >> 5, G = gridDim.x, b = blockIdx.x, w = threadIdx.x >> 5;
+  if (s.slot_order == 1) return w * G + b;
+  if (s.slot_order == 2 && s.order_ncon == 0) {
+    int n0 = 0;
+    for (int k = 0; k < ORDER_BUCKETS; k++) n0 += s.queue[16 + k];
+    if (n0 < min(nstatic, s.n)) {
+      const int Lb = n0 / G, r = n0 - Lb * G;       // blocks < r carry Lb + 1 long chains, the others Lb
+      const int myL = Lb + (b < r ? 1 : 0), long_start = b * Lb + min(b, r);
+      return w < myL ? long_start + w : n0 + (b * W - long_start) + (w - myL);
+    }
+  }
+  return b * W + w;
+}
+
 // Launch bounds (320 threads, 2 blocks per SM) cap the kernel at 96 registers.  Measured in the steady state of the bench
 // workload (profiles/r2e_warps_regs_ab.log, r2f_regs.log): 113-120 registers (bounds 512, 1) 18.2 M substeps/s, 96 registers
 // 19.1 M, 80 registers 18.4 M, 72 registers 17.4 M, 64 registers 17.2 M; the stack frame grows by only 40 bytes at 96.
@@ -274,9 +300,11 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_l
   __shared__ unsigned long long t_sum[8], t_max[8], t_round[8];
   __shared__ unsigned long long t_rounds, t_lone[8], t_lone_rounds;  // rounds in which exactly one warp of the block was active
   __shared__ unsigned int t_hist[12];  // rounds with k active warps (k = 0..11)
+  __shared__ unsigned long long t_cyc[12];  // ... and the cycles they took
+  long long t_prev = 0;
   int prev_active = 0;
   const long long t_block0 = TIMING ? clock64() : 0;
-  if (TIMING) { if (threadIdx.x < 8) { t_sum[threadIdx.x] = 0; t_max[threadIdx.x] = 0; t_round[threadIdx.x] = 0; } if (threadIdx.x == 0) { t_rounds = 0; t_lone_rounds = 0; } if (threadIdx.x < 8) t_lone[threadIdx.x] = 0; if (threadIdx.x < 12) t_hist[threadIdx.x] = 0; __syncthreads(); }
+  if (TIMING) { if (threadIdx.x < 8) { t_sum[threadIdx.x] = 0; t_max[threadIdx.x] = 0; t_round[threadIdx.x] = 0; } if (threadIdx.x == 0) { t_rounds = 0; t_lone_rounds = 0; } if (threadIdx.x < 8) t_lone[threadIdx.x] = 0; if (threadIdx.x < 12) { t_hist[threadIdx.x] = 0; t_cyc[threadIdx.x] = 0; } __syncthreads(); }
   long long t0 = 0;
 #define LS_T0() if (TIMING) t0 = clock64();
 #define LS_T1(p) if (TIMING) { unsigned long long d_ = (unsigned long long)(clock64() - t0); if (lane == 0) { atomicAdd(&t_sum[p], d_); atomicMax(&t_round[p], d_); } }
@@ -298,8 +326,7 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_l
       // first environment of a warp: static slot, so that a block starts with consecutive queue entries (environments of the
       // same class, see k_order_envs); later ones come from the shared counter, which starts behind the static slots
       const int nstatic = gridDim.x * (blockDim.x >> 5);
-      int slot = first ? (s.slot_order ? (threadIdx.x >> 5) * gridDim.x + blockIdx.x : blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))
-                       : nstatic + next_env(s.queue, lane);
+      int slot = first ? static_slot(s, nstatic) : nstatic + next_env(s.queue, lane);
       first = false;
       if (slot < s.n) {
         const int env = __ldg(s.order + slot);
@@ -319,6 +346,9 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_l
       for (int p = 0; p < 8; p++) { t_max[p] += t_round[p]; if (prev_active == 1) t_lone[p] += t_round[p]; t_round[p] = 0; }
       t_rounds++;
       t_hist[min(n_active, 11)]++;
+      const long long now = clock64();
+      if (t_prev) t_cyc[min(prev_active, 11)] += (unsigned long long)(now - t_prev);  // the round that just ended ran with prev_active warps
+      t_prev = now;
       if (prev_active == 1) t_lone_rounds++;
     }
     prev_active = n_active;
@@ -373,9 +403,10 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_l
     if (threadIdx.x == 0) { s.debug[(size_t)blockIdx.x * 32 + 16] = (float)t_rounds; s.debug[(size_t)blockIdx.x * 32 + 17] = (float)t_lone_rounds; }
     if (threadIdx.x < 8) s.debug[(size_t)blockIdx.x * 32 + 18 + threadIdx.x] = (float)t_lone[threadIdx.x];
     // block-level record (second half of the debug buffer): physics-phase duration in cycles, then rounds with k active warps
-    float* bd = s.debug + (size_t)gridDim.x * 32 + (size_t)blockIdx.x * 16;
-    if (threadIdx.x == 0) bd[0] = (float)(clock64() - t_block0);
-    if (threadIdx.x >= 1 && threadIdx.x < 13) bd[threadIdx.x] = (float)t_hist[threadIdx.x - 1];
+    float* bd = s.debug + (size_t)gridDim.x * 32 + (size_t)blockIdx.x * 32;
+    if (threadIdx.x == 0) { bd[0] = (float)(clock64() - t_block0); if (t_prev) t_cyc[min(prev_active, 11)] += (unsigned long long)(clock64() - t_prev); }
+    __syncthreads();
+    if (threadIdx.x >= 1 && threadIdx.x < 13) { bd[threadIdx.x] = (float)t_hist[threadIdx.x - 1]; bd[12 + threadIdx.x] = (float)t_cyc[threadIdx.x - 1]; }
   }
 #undef LS_T0
 #undef LS_T1

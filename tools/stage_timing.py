@@ -36,15 +36,16 @@ for name, sel in (("48 blocks with most rounds", order[:48]), ("48 blocks with f
         name, d[sel, 16].mean(), " ".join("%s %.1f" % (n, a / r / 1e3) for n, a in zip(names, d[sel, :7].sum(0))),
         " ".join("%.1f" % (b / r / 1e3) for b in d[sel, 8:15].sum(0)), d[sel, 8:15].sum() / r / 1e3))
 
-# block-level record: physics-phase duration and the number of rounds with k active warps
-bd = sim.debug.reshape(-1)[32 * 296: 32 * 296 + 16 * 296].reshape(296, 16).cpu().numpy()
-dur, hist = bd[:, 0] / 1965.0e3, bd[:, 1:13]
-last = dur.argsort()[::-1]
+# block-level record: physics-phase duration, the number of rounds with k active warps and the cycles those rounds took
 nsteps = 1  # the kernel overwrites its record: the numbers are those of the last agent step
+bd = sim.debug.reshape(-1)[32 * 296: 64 * 296].reshape(296, 32).cpu().numpy()
+dur, hist, cyc = bd[:, 0] / 1965.0e3, bd[:, 1:13], bd[:, 13:25]
+last = dur.argsort()[::-1]
 print("block physics-phase ms per agent step: mean %.2f p50 %.2f p90 %.2f max %.2f" % (dur.mean() / nsteps, np.median(dur) / nsteps, np.percentile(dur, 90) / nsteps, dur.max() / nsteps))
 for name, sel in (("all blocks", np.arange(296)), ("16 blocks with the longest physics phase", last[:16])):
-    h = hist[sel].sum(0)
+    h, c = hist[sel].sum(0), cyc[sel].sum(0)
     r = d[sel, 16].sum()
-    print("%s: ms/step %.2f, rounds/step %.0f, us/round %.1f, share of rounds by active warps (1..8): %s" % (
-        name, dur[sel].mean() / nsteps, r / len(sel) / nsteps, 1e3 * dur[sel].sum() / max(r, 1), " ".join("%d:%.0f%%" % (k, 100 * h[k] / max(h.sum(), 1)) for k in range(1, 9))))
+    print("%s: ms/step %.2f, rounds/step %.0f, us/round %.1f; rounds by active warps k = share (us per round): %s" % (
+        name, dur[sel].mean() / nsteps, r / len(sel) / nsteps, 1e3 * dur[sel].sum() / max(r, 1),
+        " ".join("%d = %.0f%% (%.0f)" % (k, 100 * h[k] / max(h.sum(), 1), c[k] / max(h[k], 1) / 1965.0) for k in range(1, 11) if h[k] > 0)))
 print("slowest blocks (id, ms/step, rounds/step):", [(int(b), round(float(dur[b] / nsteps), 2), int(d[b, 16] / nsteps)) for b in last[:10]])

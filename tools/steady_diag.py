@@ -16,7 +16,7 @@ for N in sizes:
     for i in range(PRE):
         sim.step(torch.rand((N, 6), device="cuda", generator=gen) * 2 - 1)
     torch.cuda.synchronize(); sim.step_kernel_ms(reset=True)
-    ms, sub, mx, frac, ncon, its = [], [], [], [], [], []
+    ms, sub, mx, frac, ncon, its, tops = [], [], [], [], [], [], []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tot_ms = 0.0
     for i in range(K):
@@ -25,10 +25,15 @@ for N in sizes:
         tot_ms += ev0.elapsed_time(ev1)
         info = sim.info.cpu().numpy()
         ns = info[:, I["NSUB_A"]:I["NSUB_A"] + 3].sum(1)
+        srt = np.sort(ns)[::-1]; tops.append((int(srt[0]), int(srt[1]), int(srt[7]), int(srt[63]), int(srt[295])))
         ms.append(sim.step_kernel_ms(reset=True)); sub.append(ns.sum()); mx.append(ns.max()); frac.append((ns >= 400).mean())
         ncon.append(info[:, I["NCON_MAX"]].mean()); its.append(info[:, I["SOLVER_ITERS"]].sum() / max(ns.sum(), 1))
     print("%s N=%d steps %d-%d: %.2f M substeps/s (events), kernel-phase ms mean %.2f (min %.1f max %.1f), step ms %.2f, substeps/transition %.0f, "
           "max chain mean %.0f, frac>=400 %.3f, ncon_max mean %.2f, newton iters/substep %.2f, us per round of longest chain %.1f" % (
               scene, N, PRE, PRE + K, sum(sub) / tot_ms / 1e3, np.mean(ms), np.min(ms), np.max(ms), tot_ms / K, np.mean(sub) / N, np.mean(mx), np.mean(frac),
               np.mean(ncon), np.mean(its), 1e3 * np.mean(ms) / np.mean(mx)), flush=True)
+    if os.environ.get("VERBOSE"):
+        print("per step: kernel ms | longest chain, 2nd, 8th, 64th, 296th longest | substeps/transition")
+        for a_, t_, s_ in zip(ms, tops, sub):
+            print("  %6.2f | %4d %4d %4d %4d %4d | %.0f" % ((a_,) + t_ + (s_ / N,)))
     sim.close()
