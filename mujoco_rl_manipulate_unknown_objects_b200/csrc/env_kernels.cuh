@@ -381,6 +381,8 @@ struct SimBuffers {
   const DevModel* model;
   int n;
   int order_ncon;  // longest-first order: previous-step contact count from which an environment counts as contact-heavy
+  int order_spt;   // queue order behind the gripper-closing class: 1 = shortest predicted chain first (arm only, then opening), 0 = longest first
+  int long_per_block;  // slot_order 3: gripper-closing environments per block
   int slot_order;  // lock-step kernel, first environment of a warp: 0 = consecutive queue entries per block, 1 = consecutive entries to consecutive blocks, 2 = balanced (static_slot, env_lockstep.cuh)
   int ls_mask;  // lock-step kernel: which stage boundaries carry a block barrier (bit 0 smooth | 1 constraint | 2 solve | 3 euler+kin | 4 crb)
 };

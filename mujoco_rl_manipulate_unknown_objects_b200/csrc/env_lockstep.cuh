@@ -208,10 +208,14 @@ __device__ __forceinline__ int order_class(const SimBuffers& s, const float* __r
   const float oc = actions[(size_t)env * adim + adim - 1];
   const bool open = s.state[(size_t)env * ST_STRIDE + ST_GRIPPER_OPEN] != 0.0f;
   // chain-length class: closing the gripper (~175 extra substeps) | opening it (~75) | arm only
-  const int len = (oc < 0.f && open) ? 0 : (oc > 0.f && !open) ? 1 : 2;
+  // order_spt: behind the closing class, shortest first (arm only, then opening): every environment has then STARTED by round
+  // ~150 instead of ~300, which bounds the damage of the chains nobody can predict (0.1 % of the environments run into the
+  // 400-substep arm time-out, tools/chain_predict.py: a 500-800-substep chain that starts late ends late)
+  const bool arm_only = !((oc < 0.f && open) || (oc > 0.f && !open));
+  const int len = (oc < 0.f && open) ? 0 : (arm_only ? (s.order_spt ? 1 : 2) : (s.order_spt ? 2 : 1));
   const int ncon = (int)s.info[(size_t)env * IN_STRIDE + IN_NCON_MAX];
-  if (s.order_ncon > 0) return (len == 2 ? ORDER_BUCKETS : 0) + (ncon >= s.order_ncon ? 0 : 1);  // two-level variant (sweeps)
-  if (s.order_ncon < 0) return (len == 2 ? ORDER_BUCKETS : 0) + (ORDER_BUCKETS - 1 - min(max(ncon, 0), ORDER_BUCKETS - 1));  // long | short only
+  if (s.order_ncon > 0) return (arm_only ? ORDER_BUCKETS : 0) + (ncon >= s.order_ncon ? 0 : 1);  // two-level variant (sweeps)
+  if (s.order_ncon < 0) return (arm_only ? ORDER_BUCKETS : 0) + (ORDER_BUCKETS - 1 - min(max(ncon, 0), ORDER_BUCKETS - 1));  // long | short only
   return len * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - min(max(ncon, 0), ORDER_BUCKETS - 1));  // most contacts first
 }
 __global__ void k_order_count(SimBuffers s, const float* __restrict__ actions, int adim) {
@@ -240,16 +244,26 @@ __global__ void k_order_envs(SimBuffers s, const float* __restrict__ actions, in
 //                 long chains and both of its runs are contiguous in the contact-count order (homogeneous rounds).  Once the short
 //                 environments and the shared queue are exhausted, a block is left with its few long chains, which then run at
 //                 the latency of a nearly empty SM instead of that of a full one.
+//   slot_order 3: the closing class `long_per_block` per block from block 0 on; those blocks' remaining warps and all other
+//                 blocks take the short environments.
 __device__ __forceinline__ int static_slot(const SimBuffers& s, int nstatic) {
   const int W = blockDim.x >> 5, G = gridDim.x, b = blockIdx.x, w = threadIdx.x >> 5;
   if (s.slot_order == 1) return w * G + b;
-  if (s.slot_order == 2 && s.order_ncon == 0) {
+  if (s.slot_order >= 2 && s.order_ncon == 0) {
     int n0 = 0;
     for (int k = 0; k < ORDER_BUCKETS; k++) n0 += s.queue[16 + k];
     if (n0 < min(nstatic, s.n)) {
-      const int Lb = n0 / G, r = n0 - Lb * G;       // blocks < r carry Lb + 1 long chains, the others Lb
-      const int myL = Lb + (b < r ? 1 : 0), long_start = b * Lb + min(b, r);
-      return w < myL ? long_start + w : n0 + (b * W - long_start) + (w - myL);
+      if (s.slot_order == 2) {
+        const int Lb = n0 / G, r = n0 - Lb * G;       // blocks < r carry Lb + 1 long chains, the others Lb
+        const int myL = Lb + (b < r ? 1 : 0), long_start = b * Lb + min(b, r);
+        return w < myL ? long_start + w : n0 + (b * W - long_start) + (w - myL);
+      }
+      // slot_order = 3: the closing class L per block (s.long_per_block), the block's other warps take the short environments
+      const int L = min(max(s.long_per_block, 1), W);
+      if ((n0 + L - 1) / L <= G) {
+        const int long_start = min(b * L, n0), myL = min(L, n0 - long_start);
+        return w < myL ? long_start + w : n0 + (b * W - long_start) + (w - myL);
+      }
     }
   }
   return b * W + w;

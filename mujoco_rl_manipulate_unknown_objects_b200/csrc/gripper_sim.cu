@@ -176,6 +176,8 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     b.order_ncon = getenv("GRS_ORDER_NCON") ? atoi(getenv("GRS_ORDER_NCON")) : 0;
     if (const char* e = getenv("GRS_LS_MASK")) b.ls_mask = atoi(e);
     b.slot_order = getenv("GRS_SLOT_ORDER") ? atoi(getenv("GRS_SLOT_ORDER")) : 0;
+    b.long_per_block = getenv("GRS_LONG_PER_BLOCK") ? atoi(getenv("GRS_LONG_PER_BLOCK")) : 6;
+    b.order_spt = getenv("GRS_ORDER_SPT") ? atoi(getenv("GRS_ORDER_SPT")) : 1;
     b.order = dalloc<int>(s.get(), N);
     const size_t obs_bytes = (size_t)s->C * s->H * s->W;
     s->d_obs = dalloc<unsigned char>(s.get(), N * obs_bytes);

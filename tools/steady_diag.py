@@ -25,7 +25,8 @@ for N in sizes:
         tot_ms += ev0.elapsed_time(ev1)
         info = sim.info.cpu().numpy()
         ns = info[:, I["NSUB_A"]:I["NSUB_A"] + 3].sum(1)
-        srt = np.sort(ns)[::-1]; tops.append((int(srt[0]), int(srt[1]), int(srt[7]), int(srt[63]), int(srt[295])))
+        srt = np.sort(ns)[::-1]; top3 = np.argsort(ns)[::-1][:3]
+        tops.append((int(srt[0]), int(srt[1]), int(srt[7]), int(srt[63]), int(srt[295]), " ".join("%d+%d+%d" % tuple(int(x) for x in info[e, I["NSUB_A"]:I["NSUB_A"] + 3]) for e in top3)))
         ms.append(sim.step_kernel_ms(reset=True)); sub.append(ns.sum()); mx.append(ns.max()); frac.append((ns >= 400).mean())
         ncon.append(info[:, I["NCON_MAX"]].mean()); its.append(info[:, I["SOLVER_ITERS"]].sum() / max(ns.sum(), 1))
     print("%s N=%d steps %d-%d: %.2f M substeps/s (events), kernel-phase ms mean %.2f (min %.1f max %.1f), step ms %.2f, substeps/transition %.0f, "
@@ -35,5 +36,5 @@ for N in sizes:
     if os.environ.get("VERBOSE"):
         print("per step: kernel ms | longest chain, 2nd, 8th, 64th, 296th longest | substeps/transition")
         for a_, t_, s_ in zip(ms, tops, sub):
-            print("  %6.2f | %4d %4d %4d %4d %4d | %.0f" % ((a_,) + t_ + (s_ / N,)))
+            print("  %6.2f | %4d %4d %4d %4d %4d | %.0f | top-3 (A+B+C): %s" % ((a_,) + t_[:5] + (s_ / N, t_[5])))
     sim.close()
