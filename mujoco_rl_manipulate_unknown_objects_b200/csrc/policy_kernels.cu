@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -511,6 +512,156 @@ __global__ void __launch_bounds__(C1_THREADS) k_conv1_image(const LayerArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
+// ------------------------------------------------------------------------------------------------ conv1 without im2col
+// The 8x8 stride-4 convolution read straight off the image by the tensor core's shared-memory descriptor — no im2col copy.
+// With K ordered (c, ky, kx), the K row of output pixel (oy, ox) for one (c, ky) is 8 consecutive pixels of image row
+// 4*oy + ky starting at pixel 4*ox: 16 bytes of fp16.  The canonical K-major layout WITHOUT swizzle is made of 8-row x 16-byte
+// core matrices whose rows are 16 bytes apart: the eight EVEN output pixels of a row (ox = 0, 2, .., 14 -> pixels 0, 8, .., 56)
+// are exactly one fp16 image row, i.e. one core matrix already sits in the image as it is.  The next core matrix along K
+// (ky + 1) is the next image row (leading byte offset = 128), the next 8-row group along M (oy + 1) is four image rows on
+// (stride byte offset = 512).  One MMA (M = 128, N = 32, K = 16) therefore covers all 16 x 8 even output pixels for two kernel
+// rows of one channel, 16 MMAs the whole K = 256.  The ODD output pixels (ox = 1, 3, ..) need rows that start 4 pixels = 8
+// bytes later, which a descriptor (16-byte granularity) cannot address, so the image is stored twice: the second copy shifted
+// by 8 bytes.  Per image the CTA's 256 threads convert 16 KB of uint8 to fp16 once (2 048 eight-pixel chunks, three stores
+// each) instead of building 7 200 im2col chunks; the accumulator rows come out as (oy, ox / 2) per parity tile.
+// Persistent: one CTA per SM loops over images; two stages of image copies and of TMEM accumulators, so the conversion of
+// image i + 1 and the epilogue of image i - 1 overlap the MMAs of image i; the raw bytes of the next image are prefetched into
+// registers before the epilogue.
+constexpr int CD_THREADS = 256;
+constexpr int CD_COPY = 4 * 64 * 64 * 2 + 1024;   // one fp16 copy of the four planes + slack (group 15 of the last plane reads 512 B past it)
+constexpr int CD_STAGE = 2 * CD_COPY;             // even copy, odd copy (the odd copy's first 8-byte store lands in the even copy's slack)
+constexpr size_t CD_SMEM = C1_W + 2 * CD_STAGE + 1024;
+
+// shared-memory matrix descriptor: K-major operand, no swizzle (8 x 16-byte core matrices; LBO = K step, SBO = 8-row group step)
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(CD_THREADS, 1) k_conv1_direct(const LayerArgs a, int nimg) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;            // 4 k-blocks (= channels) x [32 rows x 128 B], SWIZZLE_128B
+  uint8_t* st0 = smem + C1_W;    // stage s: even copy at st0 + s * CD_STAGE, odd copy CD_COPY behind it
+  if (tid < 32) sbias[tid] = __ldg(a.bias + tid);
+  if (tid == 0) {
+    mbar_init(&bar_mma[0], 1);
+    mbar_init(&bar_mma[1], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base_s, 128);  // stage s: columns 64 s .. 64 s + 31 even tile, + 32 .. + 63 odd tile
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+#pragma unroll
+  for (int i = 0; i < 4 * 32 * 8 / CD_THREADS; i++) {
+    const int c = i * CD_THREADS + tid, kb = c >> 8, row = (c >> 3) & 31, ch = c & 7;
+    cp_async16(smem_u32(sB + kb * 32 * 128 + row * 128 + ((ch ^ (row & 7)) << 4)), a.W + (size_t)row * a.K + kb * BK + ch * 8, true);
+  }
+  cp_async_commit();
+  // the slack behind the copies is read by the junk rows of the MMAs (results never used): keep it finite
+  for (int i = tid; i < 2 * 2 * 1024 / 16; i += CD_THREADS) {
+    const int cp = i >> 6, off = (i & 63) * 16;
+    *reinterpret_cast<uint4*>(st0 + cp * CD_COPY + (CD_COPY - 1024) + off) = make_uint4(0, 0, 0, 0);
+  }
+  const unsigned char* obs = reinterpret_cast<const unsigned char*>(a.A);
+  const size_t img_bytes = (size_t)a.C * 4096;
+  uint2 raw[8];
+  auto load_raw = [&](int n) {
+    const uint2* src = reinterpret_cast<const uint2*>(obs + (size_t)n * img_bytes);
+#pragma unroll
+    for (int j = 0; j < 8; j++) raw[j] = __ldg(src + tid + CD_THREADS * j);
+  };
+  const int stride = gridDim.x;
+  if ((int)blockIdx.x < nimg) load_raw(blockIdx.x);
+  cp_async_wait<0>();
+  constexpr uint32_t idesc = instr_desc_f16(BM, 32, false);
+  // epilogue role of this thread: tile = warp / 4 (ox parity), accumulator row m = 32 (warp % 4) + lane = 8 oy + ox / 2
+  const int etile = warp >> 2, em = 32 * (warp & 3) + lane, eoy = em >> 3, eox = 2 * (em & 7) + etile;
+  const bool evalid = eoy < 15 && eox < 15;
+  int it = 0;
+#pragma unroll 1
+  for (int n = blockIdx.x; n < nimg + stride; n += stride, it++) {
+    const int s = it & 1;
+    const bool have = n < nimg;
+    if (have) {
+      // stage s is free: the MMAs of image it - 2 were waited for by the epilogue of iteration it - 1
+      uint8_t* E = st0 + s * CD_STAGE;
+      uint8_t* O = E + CD_COPY;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int q = tid + CD_THREADS * j;  // chunk = 8 pixels; the copies are dense, so chunk q sits at byte 16 q
+        const uint4 h = u8x8_to_f16x8(raw[j]);
+        *reinterpret_cast<uint4*>(E + q * 16) = h;
+        *reinterpret_cast<uint2*>(O + q * 16 - 8) = make_uint2(h.x, h.y);  // odd copy = the image 4 pixels (8 bytes) earlier
+        *reinterpret_cast<uint2*>(O + q * 16) = make_uint2(h.z, h.w);
+      }
+      if (n + stride < nimg) load_raw(n + stride);  // in flight during the epilogue below
+      fence_async_smem();
+    }
+    __syncthreads();
+    if (have && tid == 0) {
+      tc_fence_after();
+      const uint32_t ebase = smem_u32(st0 + s * CD_STAGE), bbase = smem_u32(sB);
+#pragma unroll
+      for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+          for (int kyp = 0; kyp < 4; kyp++)
+            umma_bf16(tmem + s * 64 + t * 32, smem_desc_nosw(ebase + t * CD_COPY + c * 8192 + kyp * 256, 128, 512),
+                      smem_desc_sw128(bbase + c * 4096 + kyp * 32), idesc, (c | kyp) != 0);
+      umma_commit(&bar_mma[s]);
+    }
+    if (it > 0) {  // epilogue of the previous image (other stage) while this image's MMAs run
+      const int ps = s ^ 1, pn = n - stride;
+      mbar_wait(&bar_mma[ps], ((it - 1) >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + ps * 64 + etile * 32 + ((uint32_t)(32 * (warp & 3)) << 16), v);
+      if (evalid) {
+        uint4* out = reinterpret_cast<uint4*>(a.out + ((size_t)pn * 225 + eoy * 15 + eox) * 32);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            o[k] = pack_bf16(fmaxf(v[8 * g + 2 * k] * a.scale + sbias[8 * g + 2 * k], 0.0f), fmaxf(v[8 * g + 2 * k + 1] * a.scale + sbias[8 * g + 2 * k + 1], 0.0f));
+          out[g] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static thread_local std::string g_err;
 #define CU(call)                                                                                       \
@@ -560,7 +711,7 @@ using namespace grp;
 
 struct grp_policy {
   Shape sh{};
-  int max_envs = 0, device = 0;
+  int max_envs = 0, device = 0, num_sms = 148;
   std::vector<float> params;  // fp32 master copy, torch state_dict order (see grp_num_params)
   // device copies: bf16 K-major weights in gather order, fp32 biases
   __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wfc = nullptr, *wp0 = nullptr, *wp1 = nullptr, *wh = nullptr;
@@ -654,6 +805,8 @@ extern "C" grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t he
 #define SET_SMEM(M_, BN_, E_) CU(cudaFuncSetAttribute(k_layer<M_, BN_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer_smem_bytes<M_, BN_>()))
     SET_SMEM(CONV1, 32, EPI_RELU);
     CU(cudaFuncSetAttribute(k_conv1_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM));
+    CU(cudaFuncSetAttribute(k_conv1_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD_SMEM));
+    CU(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device));
     SET_SMEM(CONV2, 64, EPI_RELU);
     SET_SMEM(CONV3, 64, EPI_RELU);
     SET_SMEM(DENSE, 128, EPI_FEATURES);
@@ -790,7 +943,18 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     a.M = n * s.o1h * s.o1w; a.K = s.cin * 64; a.ldo = 32; a.scale = 1.0f / 255.0f;
     a.C = s.C; a.H = s.H; a.W_ = s.W; a.ih = s.H; a.iw = s.W; a.oh = s.o1h; a.ow = s.o1w;
     const bool image_kernel = s.H == 64 && s.W == 64 && s.cin == 4 && !getenv("GRP_CONV1_GENERIC");
-    if (image_kernel) {
+    const char* c1 = getenv("GRP_CONV1");  // development switch: "image" = im2col per image, "generic" = gather layer; default = descriptor-addressed
+    if (image_kernel && !(c1 && (!strcmp(c1, "image") || !strcmp(c1, "generic")))) {
+      // no im2col: the tensor core reads the (fp16) image rows through its shared-memory descriptor (k_conv1_direct)
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(std::min(n, p->num_sms)); cfg.blockDim = dim3(CD_THREADS); cfg.dynamicSmemBytes = CD_SMEM; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CU(cudaLaunchKernelEx(&cfg, k_conv1_direct, a, (int)n));
+      p->launches++;
+    } else if (image_kernel && !(c1 && !strcmp(c1, "generic"))) {
       // one image per CTA, planes staged by a bulk copy (k_conv1_image); any other observation shape takes the generic layer
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(n); cfg.blockDim = dim3(C1_THREADS); cfg.dynamicSmemBytes = C1_SMEM; cfg.stream = st;

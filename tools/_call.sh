@@ -1,8 +1,4 @@
 set -x
-export PRE=150 K=40
-run() { echo "== $*" | tee -a gpurun_out/r2q_long_per_block.log; env "$@" python tools/steady_diag.py acorn 4096 2>&1 | tee -a gpurun_out/r2q_long_per_block.log; }
-run GRS_SLOT_ORDER=0
-run GRS_SLOT_ORDER=3 GRS_LONG_PER_BLOCK=7
-run GRS_SLOT_ORDER=3 GRS_LONG_PER_BLOCK=6
-run GRS_SLOT_ORDER=3 GRS_LONG_PER_BLOCK=5
-run GRS_SLOT_ORDER=3 GRS_LONG_PER_BLOCK=4
+timeout 600 python -m pytest tests/test_policy.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r2s_policy_tests.log
+timeout 300 python tools/policy_bench.py 4096 16384 2>&1 | tee gpurun_out/r2s_policy_bench.log
+GRP_CONV1=image timeout 300 python tools/policy_bench.py 4096 2>&1 | tee -a gpurun_out/r2s_policy_bench.log
