@@ -99,6 +99,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the descriptors as 32-bit halves (only the low word — the 14-bit start address — changes between the MMAs of a
+// tile: one 32-bit add per operand instead of a 64-bit one) and the accumulate flag as a compile-time constant
+template <int ACC>
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "n"(ACC)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                         // STAGES x [128 rows x 128 B]
   uint8_t* sB = smem + STAGES * BM * 128;     // STAGES x [BN rows x 128 B]
-  __shared__ float sbias[BN];  // this CTA's slice of the bias (a parameter, not an activation: safe to read before griddepcontrol.wait)
+  __shared__ __align__(16) float sbias[BN];  // this CTA's slice of the bias (a parameter, not an activation: safe to read before griddepcontrol.wait)
   for (int i = tid; i < BN; i += THREADS) sbias[i] = __ldg(a.bias + blockIdx.y * BN + i);
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) mbar_init(&bar_stage[s], 1);
@@ -371,10 +384,13 @@ __global__ void __launch_bounds__(THREADS) k_layer(const LayerArgs a) {
       tmem_ld16(trow + c0, v);
       if (row < a.M) {
         uint32_t o[8];
+        float bv[16];  // four 16-byte broadcast loads instead of sixteen scalar ones
+#pragma unroll
+        for (int k = 0; k < 4; k++) *reinterpret_cast<float4*>(bv + 4 * k) = *reinterpret_cast<const float4*>(sbias + c0 + 4 * k);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-          const float x = fmaxf(v[2 * k] * a.scale + sbias[c0 + 2 * k], 0.0f);
-          const float y = fmaxf(v[2 * k + 1] * a.scale + sbias[c0 + 2 * k + 1], 0.0f);
+          const float x = fmaxf(fmaf(v[2 * k], a.scale, bv[2 * k]), 0.0f);
+          const float y = fmaxf(fmaf(v[2 * k + 1], a.scale, bv[2 * k + 1]), 0.0f);
           o[k] = pack_bf16(x, y);
         }
         uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)row * a.ldo + n0 + c0);
@@ -516,21 +532,26 @@ __global__ void __launch_bounds__(C1_THREADS) k_conv1_image(const LayerArgs a) {
 // The 8x8 stride-4 convolution read straight off the image by the tensor core's shared-memory descriptor — no im2col copy.
 // With K ordered (c, ky, kx), the K row of output pixel (oy, ox) for one (c, ky) is 8 consecutive pixels of image row
 // 4*oy + ky starting at pixel 4*ox: 16 bytes of fp16.  The canonical K-major layout WITHOUT swizzle is made of 8-row x 16-byte
-// core matrices whose rows are 16 bytes apart: the eight EVEN output pixels of a row (ox = 0, 2, .., 14 -> pixels 0, 8, .., 56)
+// core matrices whose rows are 16 bytes apart: the eight EVEN output pixels of a row (ox = 2r -> pixels 8r .. 8r + 7, chunk r)
 // are exactly one fp16 image row, i.e. one core matrix already sits in the image as it is.  The next core matrix along K
 // (ky + 1) is the next image row (leading byte offset = 128), the next 8-row group along M (oy + 1) is four image rows on
-// (stride byte offset = 512).  One MMA (M = 128, N = 32, K = 16) therefore covers all 16 x 8 even output pixels for two kernel
-// rows of one channel, 16 MMAs the whole K = 256.  The ODD output pixels (ox = 1, 3, ..) need rows that start 4 pixels = 8
-// bytes later, which a descriptor (16-byte granularity) cannot address, so the image is stored twice: the second copy shifted
-// by 8 bytes.  Per image the CTA's 256 threads convert 16 KB of uint8 to fp16 once (2 048 eight-pixel chunks, three stores
-// each) instead of building 7 200 im2col chunks; the accumulator rows come out as (oy, ox / 2) per parity tile.
+// (stride byte offset = 512).  One MMA (M = 128, K = 16) therefore covers 16 x 8 chunk rows for two kernel rows of one
+// channel, 16 MMAs the whole K = 256.
+// The ODD output pixels (ox = 2r + 1) need the 8 pixels from 8r + 4 on: the upper half of chunk r and the lower half of chunk
+// r + 1 — not addressable as one row (descriptors have 16-byte granularity).  They are computed from whole chunks with
+// zero-padded weights: odd(r) = chunk r x Wa + chunk r + 1 x Wb with Wa = [0 0 0 0 w0 w1 w2 w3], Wb = [w4 w5 w6 w7 0 0 0 0].
+// All three products of a chunk row share the A operand, so they are ONE MMA with N = 96: B = [W ; Wa ; Wb], accumulator
+// columns 0-31 = even(r), 32-63 = chunk r x Wa, 64-95 = chunk r x Wb, and the epilogue adds column block 2 of accumulator row
+// m + 1 (a register shuffle from the next lane: rows are lanes) to column block 1 of row m.  16 MMAs per image; the image is read
+// from shared memory once per 96 output columns (one N = 32 MMA per product was bound by the tensor core's operand reads,
+// 240 KB per image); ONE fp16 copy of the image, one 16-byte store per 8-pixel chunk instead of 7 200 im2col chunks per image.
 // Persistent: one CTA per SM loops over images; two stages of image copies and of TMEM accumulators, so the conversion of
-// image i + 1 and the epilogue of image i - 1 overlap the MMAs of image i; the raw bytes of the next image are prefetched into
-// registers before the epilogue.
-constexpr int CD_THREADS = 256;
-constexpr int CD_COPY = 4 * 64 * 64 * 2 + 1024;   // one fp16 copy of the four planes + slack (group 15 of the last plane reads 512 B past it)
-constexpr int CD_STAGE = 2 * CD_COPY;             // even copy, odd copy (the odd copy's first 8-byte store lands in the even copy's slack)
-constexpr size_t CD_SMEM = C1_W + 2 * CD_STAGE + 1024;
+// image i + 1 and the epilogue of image i - 1 overlap the MMAs of image i; raw bytes are prefetched two images ahead.
+constexpr int CD_THREADS = 512;                   // worker threads (convert + epilogue)
+constexpr int CD_CHUNKS = 2048 / CD_THREADS;      // eight-pixel chunks per worker and image
+constexpr int CD_STAGE = 4 * 64 * 64 * 2 + 1024;  // the fp16 copy of the four planes + slack (group 15 of the last plane reads 512 B past it)
+constexpr int CD_W = 4 * 96 * 128;                // 4 k-blocks (= input channels) x [96 rows = W | Wa | Wb] x 128 B, SWIZZLE_128B
+constexpr size_t CD_SMEM = CD_W + 2 * CD_STAGE + 1024;
 
 // shared-memory matrix descriptor: K-major operand, no swizzle (8 x 16-byte core matrices; LBO = K step, SBO = 8-row group step)
 __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -540,6 +561,14 @@ __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
   return d;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -555,111 +584,285 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(CD_THREADS, 1) k_conv1_direct(const LayerArgs a, int nimg) {
+template <bool DEDICATED>  // true: an extra warp issues the MMAs; false: thread 0 does
+__global__ void __launch_bounds__(CD_THREADS + (DEDICATED ? 32 : 0), 1) k_conv1_direct(const LayerArgs a, int nimg) {
+  constexpr int NT = CD_THREADS + (DEDICATED ? 32 : 0), ISSUER = DEDICATED ? CD_THREADS : 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_mma[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float sbias[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sB = smem;            // 4 k-blocks (= channels) x [32 rows x 128 B], SWIZZLE_128B
-  uint8_t* st0 = smem + C1_W;    // stage s: even copy at st0 + s * CD_STAGE, odd copy CD_COPY behind it
-  if (tid < 32) sbias[tid] = __ldg(a.bias + tid);
+  uint8_t* sB = smem;            // [4 k-blocks][96 rows: W | Wa | Wb][128 B]
+  uint8_t* st0 = smem + CD_W;    // stage s: the fp16 image at st0 + s * CD_STAGE
   if (tid == 0) {
     mbar_init(&bar_mma[0], 1);
     mbar_init(&bar_mma[1], 1);
     fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(&tmem_base_s, 128);  // stage s: columns 64 s .. 64 s + 31 even tile, + 32 .. + 63 odd tile
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);  // stage s: columns 128 s .. 128 s + 95
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-#pragma unroll
-  for (int i = 0; i < 4 * 32 * 8 / CD_THREADS; i++) {
-    const int c = i * CD_THREADS + tid, kb = c >> 8, row = (c >> 3) & 31, ch = c & 7;
-    cp_async16(smem_u32(sB + kb * 32 * 128 + row * 128 + ((ch ^ (row & 7)) << 4)), a.W + (size_t)row * a.K + kb * BK + ch * 8, true);
+  for (int i = tid; i < 4 * 96 * 8; i += NT) {  // rows 0-31 W, 32-63 Wa, 64-95 Wb: three consecutive [32][K] matrices behind a.W
+    const int kb = i / 768, c = i - kb * 768, row = c >> 3, ch = c & 7;
+    cp_async16(smem_u32(sB + kb * 96 * 128 + row * 128 + ((ch ^ (row & 7)) << 4)), a.W + (size_t)row * a.K + kb * BK + ch * 8, true);
   }
   cp_async_commit();
   // the slack behind the copies is read by the junk rows of the MMAs (results never used): keep it finite
-  for (int i = tid; i < 2 * 2 * 1024 / 16; i += CD_THREADS) {
-    const int cp = i >> 6, off = (i & 63) * 16;
-    *reinterpret_cast<uint4*>(st0 + cp * CD_COPY + (CD_COPY - 1024) + off) = make_uint4(0, 0, 0, 0);
-  }
+  for (int i = tid; i < 2 * 1024 / 16; i += NT) *reinterpret_cast<uint4*>(st0 + (i >> 6) * CD_STAGE + (CD_STAGE - 1024) + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
   const unsigned char* obs = reinterpret_cast<const unsigned char*>(a.A);
   const size_t img_bytes = (size_t)a.C * 4096;
-  uint2 raw[8];
-  auto load_raw = [&](int n) {
-    const uint2* src = reinterpret_cast<const uint2*>(obs + (size_t)n * img_bytes);
-#pragma unroll
-    for (int j = 0; j < 8; j++) raw[j] = __ldg(src + tid + CD_THREADS * j);
-  };
+  // raw bytes of the next two images of this CTA, in registers
+  uint2 rawA[CD_CHUNKS], rawB[CD_CHUNKS];
   const int stride = gridDim.x;
-  if ((int)blockIdx.x < nimg) load_raw(blockIdx.x);
+  const bool worker = tid < CD_THREADS;  // the extra warp (if any) only issues the MMAs
+  auto load_raw = [&](uint2 (&raw)[CD_CHUNKS], int n) {
+    if (n < nimg && worker) {
+      const uint2* src = reinterpret_cast<const uint2*>(obs + (size_t)n * img_bytes);
+#pragma unroll
+      for (int j = 0; j < CD_CHUNKS; j++) raw[j] = __ldg(src + tid + CD_THREADS * j);
+    }
+  };
+  load_raw(rawA, blockIdx.x);
+  load_raw(rawB, blockIdx.x + stride);
   cp_async_wait<0>();
-  constexpr uint32_t idesc = instr_desc_f16(BM, 32, false);
-  // epilogue role of this thread: tile = warp / 4 (ox parity), accumulator row m = 32 (warp % 4) + lane = 8 oy + ox / 2
-  const int etile = warp >> 2, em = 32 * (warp & 3) + lane, eoy = em >> 3, eox = 2 * (em & 7) + etile;
-  const bool evalid = eoy < 15 && eox < 15;
-  int it = 0;
-#pragma unroll 1
-  for (int n = blockIdx.x; n < nimg + stride; n += stride, it++) {
-    const int s = it & 1;
+  constexpr uint32_t idesc = instr_desc_f16(BM, 96, false);
+  // epilogue role of this thread: accumulator row m = 32 (warp % 4) + lane = 8 oy + r, output channels 8 (warp / 4) .. + 7 of the
+  // two output pixels ox = 2r and 2r + 1
+  const int eq = (warp >> 2) & 3, em = 32 * (warp & 3) + lane, eoy = em >> 3, er = em & 7;
+  const bool evalid = eoy < 15;
+  float eb[8];  // this thread's biases, in registers (a shared-memory load per accumulator element made the epilogue MIO-bound)
+#pragma unroll
+  for (int k = 0; k < 8; k++) eb[k] = __ldg(a.bias + eq * 8 + k);
+  const float escale = a.scale;
+  // one image: convert into stage s, start its MMAs, then finish the previous image (other stage) while they run
+  auto step = [&](uint2 (&raw)[CD_CHUNKS], const int s, const int n, const int it) {
     const bool have = n < nimg;
-    if (have) {
+    if (have && worker) {
       // stage s is free: the MMAs of image it - 2 were waited for by the epilogue of iteration it - 1
       uint8_t* E = st0 + s * CD_STAGE;
-      uint8_t* O = E + CD_COPY;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int q = tid + CD_THREADS * j;  // chunk = 8 pixels; the copies are dense, so chunk q sits at byte 16 q
-        const uint4 h = u8x8_to_f16x8(raw[j]);
-        *reinterpret_cast<uint4*>(E + q * 16) = h;
-        *reinterpret_cast<uint2*>(O + q * 16 - 8) = make_uint2(h.x, h.y);  // odd copy = the image 4 pixels (8 bytes) earlier
-        *reinterpret_cast<uint2*>(O + q * 16) = make_uint2(h.z, h.w);
-      }
-      if (n + stride < nimg) load_raw(n + stride);  // in flight during the epilogue below
+      for (int j = 0; j < CD_CHUNKS; j++) *reinterpret_cast<uint4*>(E + (tid + CD_THREADS * j) * 16) = u8x8_to_f16x8(raw[j]);  // the copy is dense: chunk q at byte 16 q
+      load_raw(raw, n + 2 * stride);  // in flight for two iterations
       fence_async_smem();
     }
     __syncthreads();
-    if (have && tid == 0) {
+    if (have && tid == ISSUER) {
+      // 16 MMAs (M = 128, N = 96, K = 16); every descriptor is a constant 16-byte-unit offset away from the stage's first one
       tc_fence_after();
-      const uint32_t ebase = smem_u32(st0 + s * CD_STAGE), bbase = smem_u32(sB);
+      const uint64_t a0 = smem_desc_nosw(smem_u32(st0 + s * CD_STAGE), 128, 512), b0 = smem_desc_sw128(smem_u32(sB));
+      const uint32_t alo = (uint32_t)a0, ahi = (uint32_t)(a0 >> 32), blo = (uint32_t)b0, bhi = (uint32_t)(b0 >> 32), td = tmem + s * 128;
 #pragma unroll
-      for (int t = 0; t < 2; t++)
+      for (int c = 0; c < 4; c++)
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-          for (int kyp = 0; kyp < 4; kyp++)
-            umma_bf16(tmem + s * 64 + t * 32, smem_desc_nosw(ebase + t * CD_COPY + c * 8192 + kyp * 256, 128, 512),
-                      smem_desc_sw128(bbase + c * 4096 + kyp * 32), idesc, (c | kyp) != 0);
+        for (int kyp = 0; kyp < 4; kyp++) {
+          if ((c | kyp) == 0) umma_bf16_lo<0>(td, alo + ((c * 8192 + kyp * 256) >> 4), ahi, blo + ((c * 96 * 128 + kyp * 32) >> 4), bhi, idesc);
+          else umma_bf16_lo<1>(td, alo + ((c * 8192 + kyp * 256) >> 4), ahi, blo + ((c * 96 * 128 + kyp * 32) >> 4), bhi, idesc);
+        }
       umma_commit(&bar_mma[s]);
     }
-    if (it > 0) {  // epilogue of the previous image (other stage) while this image's MMAs run
+    if (it > 0 && worker) {  // epilogue of the previous image (other stage) while this image's MMAs run
       const int ps = s ^ 1, pn = n - stride;
       mbar_wait(&bar_mma[ps], ((it - 1) >> 1) & 1);
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem + ps * 64 + etile * 32 + ((uint32_t)(32 * (warp & 3)) << 16), v);
+      float ve[8], va[8], vb[8];
+      {
+        const uint32_t tb = tmem + ps * 128 + eq * 8 + ((uint32_t)(32 * (warp & 3)) << 16);
+        tmem_ld8(tb, ve);
+        tmem_ld8(tb + 32, va);
+        tmem_ld8(tb + 64, vb);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) va[k] += __shfl_down_sync(0xffffffffu, vb[k], 1);  // odd(r) = chunk r x Wa + chunk r + 1 x Wb (row m + 1; r = 7 has no odd pixel)
       if (evalid) {
-        uint4* out = reinterpret_cast<uint4*>(a.out + ((size_t)pn * 225 + eoy * 15 + eox) * 32);
+        uint32_t oe[4], oo[4];
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-          uint32_t o[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            o[k] = pack_bf16(fmaxf(v[8 * g + 2 * k] * a.scale + sbias[8 * g + 2 * k], 0.0f), fmaxf(v[8 * g + 2 * k + 1] * a.scale + sbias[8 * g + 2 * k + 1], 0.0f));
-          out[g] = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int k = 0; k < 4; k++) {
+          oe[k] = pack_bf16(fmaxf(fmaf(ve[2 * k], escale, eb[2 * k]), 0.0f), fmaxf(fmaf(ve[2 * k + 1], escale, eb[2 * k + 1]), 0.0f));
+          oo[k] = pack_bf16(fmaxf(fmaf(va[2 * k], escale, eb[2 * k]), 0.0f), fmaxf(fmaf(va[2 * k + 1], escale, eb[2 * k + 1]), 0.0f));
+        }
+        if (a.ldo == 32) {  // dense [225][32] rows (the gather-based conv2)
+          __nv_bfloat16* row = a.out + ((size_t)pn * 225 + eoy * 15 + 2 * er) * 32 + eq * 8;
+          *reinterpret_cast<uint4*>(row) = make_uint4(oe[0], oe[1], oe[2], oe[3]);
+          if (er < 7) *reinterpret_cast<uint4*>(row + 32) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+        } else {
+          // the layout conv2's descriptor reads: [15][16 px][32 ch], 128-byte lines of two pixels (2r, 2r + 1), chunk j of line l at j ^ (l & 7)
+          const int l = eoy * 8 + er;
+          uint8_t* line = reinterpret_cast<uint8_t*>(a.out) + (size_t)pn * 16384 + l * 128;
+          *reinterpret_cast<uint4*>(line + ((eq ^ (l & 7)) << 4)) = make_uint4(oe[0], oe[1], oe[2], oe[3]);
+          if (er < 7) *reinterpret_cast<uint4*>(line + (((4 + eq) ^ (l & 7)) << 4)) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
         }
       }
       tc_fence_before();
     }
+  };
+  // the extra pass behind the last image runs its epilogue; iterations come in pairs so that stage and register set are static
+#pragma unroll 1
+  for (int n = blockIdx.x, it = 0; n < nimg + stride; n += 2 * stride, it += 2) {
+    step(rawA, 0, n, it);
+    if (n < nimg) step(rawB, 1, n + stride, it + 1);
   }
   __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ conv2 / conv3 without im2col
+// Same idea with the 128-byte swizzle.  The previous layer leaves its activations in HBM in exactly the byte order the tensor
+// core wants to find them in shared memory (padded NHWC lines of 128 bytes, 16-byte chunks XOR-swizzled by the line index), so
+//   * a pair of images is ONE contiguous bulk copy (cp.async.bulk, the TMA engine's 1-D path, completing on an mbarrier),
+//   * every k-block of the convolution is a start address inside that copy: the A rows of output pixels ox = 0..7 of one
+//     output row are 8 consecutive 128-byte lines (conv2: 4x4 stride 2 on [15][16 px][32 ch], a line = two pixels, k-block
+//     (ky, kx pair) starts ky rows + kx-pair lines in; conv3: 3x3 stride 1 on [8][8 px][64 ch], a line = one pixel, k-block
+//     (ky, kx) starts ky rows + kx lines in), the next output row is the next 8-row group (stride byte offset = two image
+//     rows / one image row), and the second image of the pair follows at 8 groups' distance, so M = 128 is two images.
+// The weights stay resident in shared memory for the whole (persistent) CTA.  Warp-specialised: one producer thread (bulk
+// copies, STAGES deep), one MMA-issuer thread (32 / 36 tcgen05.mma per image pair into one of two TMEM accumulators, stage and
+// accumulator hand-over by tcgen05.commit on mbarriers), eight epilogue warps (tcgen05.ld, bias + ReLU, bf16, store in the
+// layout the next layer reads) that overlap the MMAs of the next pair.
+template <int LAYER> struct DirectConv;
+template <> struct DirectConv<2> {  // 32 -> 64 channels, 4x4 stride 2, [15][16][32] (16 KB per image) -> [8][8][64] (8 KB per image)
+  static constexpr int IMG_IN = 16384, NKB = 8, SBO = 2048, OUT = 6, STAGES = 3, WROWS = 64;
+  __device__ static constexpr int kb_offset(int kb) { return (kb >> 1) * 1024 + (kb & 1) * 128; }
+};
+template <> struct DirectConv<3> {  // 64 -> 64 channels, 3x3 stride 1, [8][8][64] -> dense [16][64] (the linear layer's flatten order)
+  static constexpr int IMG_IN = 8192, NKB = 9, SBO = 1024, OUT = 4, STAGES = 4, WROWS = 64;
+  __device__ static constexpr int kb_offset(int kb) { return ((kb / 3) * 8 + (kb % 3)) * 128; }
+};
+constexpr int DC_THREADS = 320;  // warps 0-7 epilogue, warp 8 producer, warp 9 MMA issuer
+template <int LAYER>
+constexpr size_t dc_smem() { return (size_t)DirectConv<LAYER>::NKB * 64 * 128 + (size_t)DirectConv<LAYER>::STAGES * 2 * DirectConv<LAYER>::IMG_IN + 8192 + 1024; }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+
+template <int LAYER>
+__global__ void __launch_bounds__(DC_THREADS, 1) k_conv_direct(const LayerArgs a, int nimg) {
+  using L = DirectConv<LAYER>;
+  constexpr int STAGES = L::STAGES, PAIR = 2 * L::IMG_IN;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;                                  // NKB k-blocks x [64 rows x 128 B], SWIZZLE_128B
+  uint8_t* sA = smem + L::NKB * 64 * 128;              // STAGES x image pair (+ 8 KB behind: the junk groups of the last pair read past it)
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 8); }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base_s, 128);  // two accumulators of 64 columns
+  // weights: a parameter, not an activation — staged before the dependency wait
+  for (int i = tid; i < L::NKB * 64 * 8; i += DC_THREADS) {
+    const int kb = i >> 9, row = (i >> 3) & 63, ch = i & 7;
+    cp_async16(smem_u32(sW + kb * 64 * 128 + row * 128 + ((ch ^ (row & 7)) << 4)), a.W + (size_t)row * a.K + kb * BK + ch * 8, true);
+  }
+  cp_async_commit();
+  for (int i = tid; i < 8192 / 16; i += DC_THREADS) *reinterpret_cast<uint4*>(sA + STAGES * PAIR + i * 16) = make_uint4(0, 0, 0, 0);
+  cp_async_wait<0>();
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const int npair = (nimg + 1) >> 1;
+  if (warp == 8) {
+    // ---- producer: one bulk copy per image pair
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.A);
+      int k = 0;
+      for (int pr = blockIdx.x; pr < npair; pr += gridDim.x, k++) {
+        const int s = k % STAGES;
+        mbar_wait(&bar_empty[s], ((k / STAGES) & 1) ^ 1);
+        const uint32_t bytes = (2 * pr + 1 < nimg) ? PAIR : L::IMG_IN;  // the last pair of an odd batch is one image (the other half keeps stale, unused rows)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_full[s])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sA + s * PAIR)), "l"(src + (size_t)pr * PAIR), "r"(bytes), "r"(smem_u32(&bar_full[s])) : "memory");
+      }
+    }
+  } else if (warp == 9) {
+    // ---- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_f16(BM, 64, true);
+      const uint64_t w0 = smem_desc_sw128(smem_u32(sW));
+      int k = 0;
+      for (int pr = blockIdx.x; pr < npair; pr += gridDim.x, k++) {
+        const int s = k % STAGES, t = k & 1;
+        mbar_wait(&bar_tempty[t], ((k >> 1) & 1) ^ 1);
+        mbar_wait(&bar_full[s], (k / STAGES) & 1);
+        tc_fence_after();
+        // A descriptor: 8-row groups SBO apart (the 1024 of smem_desc_sw128 replaced)
+        uint64_t a0 = smem_desc_sw128(smem_u32(sA + s * PAIR));
+        a0 = (a0 & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(L::SBO >> 4) << 32);
+#pragma unroll
+        for (int kb = 0; kb < L::NKB; kb++)
+#pragma unroll
+          for (int k16 = 0; k16 < 4; k16++)
+            umma_bf16(tmem + t * 64, a0 + (uint64_t)((L::kb_offset(kb) + k16 * 32) >> 4), w0 + (uint64_t)((kb * 64 * 128 + k16 * 32) >> 4), idesc, (kb | k16) != 0);
+        umma_commit(&bar_empty[s]);
+        umma_commit(&bar_tfull[t]);
+      }
+    }
+  } else {
+    // ---- epilogue: accumulator row m = 32 (warp % 4) + lane = 64 * image-in-pair + 8 * oy + ox, columns 32 (warp / 4) .. + 31
+    const int half = warp >> 2, m = 32 * (warp & 3) + lane, img = m >> 6, oy = (m >> 3) & 7, ox = m & 7;
+    const bool valid = oy < L::OUT && ox < L::OUT;
+    float eb[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) eb[i] = __ldg(a.bias + half * 32 + i);
+    int k = 0;
+    for (int pr = blockIdx.x; pr < npair; pr += gridDim.x, k++) {
+      const int t = k & 1, n = 2 * pr + img;
+      mbar_wait(&bar_tfull[t], (k >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + t * 64 + half * 32 + ((uint32_t)(32 * (warp & 3)) << 16), v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[t]);  // the accumulator is in registers: the next pair's MMAs may overwrite it
+      if (valid && n < nimg) {
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) o[i] = pack_bf16(fmaxf(v[2 * i] + eb[2 * i], 0.0f), fmaxf(v[2 * i + 1] + eb[2 * i + 1], 0.0f));
+        if (LAYER == 2) {
+          // -> [8][8 px][64 ch] lines of 128 bytes, chunk j of line l stored at position j ^ (l & 7) (what conv3's descriptor expects)
+          const int l = oy * 8 + ox;
+          uint8_t* line = reinterpret_cast<uint8_t*>(a.out) + (size_t)n * 8192 + l * 128;
+#pragma unroll
+          for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(line + (((half * 4 + j) ^ (l & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(a.out + ((size_t)n * 16 + oy * 4 + ox) * 64 + half * 32);
+#pragma unroll
+          for (int j = 0; j < 4; j++) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// padded / swizzled activations -> dense NHWC (tests and debugging only: grp_buffer("act1" / "act2"))
+__global__ void k_unpack_act(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, int nimg, int layer) {
+  // layer 1: [15][16 px][32 ch] lines of two pixels -> [225][32]; layer 2: [8][8 px][64 ch] lines of one pixel -> [36][64]
+  const int hw = layer == 1 ? 15 : 6, C = layer == 1 ? 32 : 64, img_bytes = layer == 1 ? 16384 : 8192;
+  const long total = (long)nimg * hw * hw * (C / 8);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % (C / 8));
+    const long px = i / (C / 8);
+    const int x = (int)(px % hw), y = (int)((px / hw) % hw);
+    const long n = px / (hw * hw);
+    const int l = layer == 1 ? y * 8 + (x >> 1) : y * 8 + x, j = layer == 1 ? (x & 1) * 4 + c8 : c8;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + n * img_bytes + l * 128 + ((j ^ (l & 7)) << 4));
+    *reinterpret_cast<uint4*>(dst + (px * C + c8 * 8)) = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -718,6 +921,9 @@ struct grp_policy {
   float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *bfc = nullptr, *bp0 = nullptr, *bp1 = nullptr, *bh = nullptr;
   // activations (bf16 NHWC) and outputs
   __nv_bfloat16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *feat = nullptr, *h1 = nullptr, *h2 = nullptr;
+  __nv_bfloat16 *act1_dense = nullptr, *act2_dense = nullptr;  // grp_buffer("act1" / "act2") when the descriptor-addressed chain left them padded + swizzled
+  bool direct_last = false;   // layout of act1 / act2 after the last forward
+  int last_n = 0;
   float *mu = nullptr, *log_std = nullptr;
   std::vector<void*> owned;
   cudaStream_t stream = nullptr;
@@ -787,15 +993,15 @@ extern "C" grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t he
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     const size_t N = max_envs;
     p->params.assign(layout_of(s).total, 0.0f);
-    p->w1 = palloc<__nv_bfloat16>(p.get(), 32 * (size_t)s.cin * 64); p->b1 = palloc<float>(p.get(), 32);
+    p->w1 = palloc<__nv_bfloat16>(p.get(), 3 * 32 * (size_t)s.cin * 64); /* W | Wa | Wb (k_conv1_direct) */ p->b1 = palloc<float>(p.get(), 32);
     p->w2 = palloc<__nv_bfloat16>(p.get(), 64 * 512); p->b2 = palloc<float>(p.get(), 64);
     p->w3 = palloc<__nv_bfloat16>(p.get(), 64 * 576); p->b3 = palloc<float>(p.get(), 64);
     p->wfc = palloc<__nv_bfloat16>(p.get(), 512 * (size_t)s.nflat); p->bfc = palloc<float>(p.get(), 512);
     p->wp0 = palloc<__nv_bfloat16>(p.get(), 256 * (size_t)FEAT_LD); p->bp0 = palloc<float>(p.get(), 256);
     p->wp1 = palloc<__nv_bfloat16>(p.get(), 256 * 256); p->bp1 = palloc<float>(p.get(), 256);
     p->wh = palloc<__nv_bfloat16>(p.get(), HEAD_N * 256); p->bh = palloc<float>(p.get(), HEAD_N);
-    p->act1 = palloc<__nv_bfloat16>(p.get(), N * s.o1h * s.o1w * 32);
-    p->act2 = palloc<__nv_bfloat16>(p.get(), N * s.o2h * s.o2w * 64);
+    p->act1 = palloc<__nv_bfloat16>(p.get(), std::max(N * s.o1h * s.o1w * 32, (N + 2) * 8192));  // dense [225][32] or padded [15][16][32] per image
+    p->act2 = palloc<__nv_bfloat16>(p.get(), std::max(N * s.o2h * s.o2w * 64, (N + 2) * 4096));  // dense [36][64] or padded [8][8][64] per image
     p->act3 = palloc<__nv_bfloat16>(p.get(), N * s.nflat);
     p->feat = palloc<__nv_bfloat16>(p.get(), N * FEAT_LD);
     p->h1 = palloc<__nv_bfloat16>(p.get(), N * 256);
@@ -805,7 +1011,10 @@ extern "C" grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t he
 #define SET_SMEM(M_, BN_, E_) CU(cudaFuncSetAttribute(k_layer<M_, BN_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer_smem_bytes<M_, BN_>()))
     SET_SMEM(CONV1, 32, EPI_RELU);
     CU(cudaFuncSetAttribute(k_conv1_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM));
-    CU(cudaFuncSetAttribute(k_conv1_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD_SMEM));
+    CU(cudaFuncSetAttribute(k_conv_direct<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem<2>()));
+    CU(cudaFuncSetAttribute(k_conv_direct<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem<3>()));
+    CU(cudaFuncSetAttribute(k_conv1_direct<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD_SMEM));
+    CU(cudaFuncSetAttribute(k_conv1_direct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD_SMEM));
     CU(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device));
     SET_SMEM(CONV2, 64, EPI_RELU);
     SET_SMEM(CONV3, 64, EPI_RELU);
@@ -846,9 +1055,18 @@ extern "C" int32_t grp_set_params(grp_policy* p, const float* host, int64_t coun
     const float* P = p->params.data();
     std::vector<uint16_t> h;
     // conv1 [32][cin][8][8]: K order (c, ky, kx) is torch's own
-    h.resize(32 * (size_t)s.cin * 64);
-    for (size_t i = 0; i < h.size(); i++) h[i] = f2h(P[L.c1w + i]);  // fp16: the uint8 pixels convert to fp16 exactly and cheaply
-    upload_bf16(p->w1, h);
+    {
+      const size_t n1 = 32 * (size_t)s.cin * 64;
+      h.assign(3 * n1, 0);
+      for (size_t i = 0; i < n1; i++) {  // fp16: the uint8 pixels convert to fp16 exactly and cheaply
+        const uint16_t v = f2h(P[L.c1w + i]);
+        const size_t kx = i & 7;
+        h[i] = v;
+        if (kx < 4) h[n1 + i + 4] = v;          // Wa = [0 0 0 0 w0 w1 w2 w3] per kernel row
+        else h[2 * n1 + i - 4] = v;             // Wb = [w4 w5 w6 w7 0 0 0 0]
+      }
+      upload_bf16(p->w1, h);
+    }
     // conv2 [64][32][4][4] -> [64][(ky, kx, c)]
     h.assign(64 * 512, 0);
     for (int o = 0; o < 64; o++)
@@ -944,15 +1162,22 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     a.C = s.C; a.H = s.H; a.W_ = s.W; a.ih = s.H; a.iw = s.W; a.oh = s.o1h; a.ow = s.o1w;
     const bool image_kernel = s.H == 64 && s.W == 64 && s.cin == 4 && !getenv("GRP_CONV1_GENERIC");
     const char* c1 = getenv("GRP_CONV1");  // development switch: "image" = im2col per image, "generic" = gather layer; default = descriptor-addressed
-    if (image_kernel && !(c1 && (!strcmp(c1, "image") || !strcmp(c1, "generic")))) {
+    const char* cc = getenv("GRP_CONV23");  // "gather" = im2col-on-the-fly conv2 / conv3 (k_layer); default = descriptor-addressed when conv1 is
+    const bool direct1 = image_kernel && !(c1 && (!strcmp(c1, "image") || !strcmp(c1, "generic")));
+    const bool direct23 = direct1 && !(cc && !strcmp(cc, "gather"));
+    p->direct_last = direct23; p->last_n = n;
+    if (direct23) a.ldo = 0;  // conv1 leaves act1 in the padded, swizzled layout conv2's descriptor reads
+    if (direct1) {
       // no im2col: the tensor core reads the (fp16) image rows through its shared-memory descriptor (k_conv1_direct)
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(std::min(n, p->num_sms)); cfg.blockDim = dim3(CD_THREADS); cfg.dynamicSmemBytes = CD_SMEM; cfg.stream = st;
+      const bool dedicated = getenv("GRP_CONV1_ISSUER") && atoi(getenv("GRP_CONV1_ISSUER")) != 0;
+      cfg.gridDim = dim3(std::min(n, p->num_sms)); cfg.blockDim = dim3(CD_THREADS + (dedicated ? 32 : 0)); cfg.dynamicSmemBytes = CD_SMEM; cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      CU(cudaLaunchKernelEx(&cfg, k_conv1_direct, a, (int)n));
+      if (dedicated) CU(cudaLaunchKernelEx(&cfg, k_conv1_direct<true>, a, (int)n));
+      else CU(cudaLaunchKernelEx(&cfg, k_conv1_direct<false>, a, (int)n));
       p->launches++;
     } else if (image_kernel && !(c1 && !strcmp(c1, "generic"))) {
       // one image per CTA, planes staged by a bulk copy (k_conv1_image); any other observation shape takes the generic layer
@@ -967,18 +1192,30 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     } else {
       launch_layer<CONV1, 32, EPI_RELU>(p, a, 32, st);
     }
+    auto launch_direct = [&](auto kernel, size_t smem_bytes, const LayerArgs& la) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(std::min((n + 1) / 2, p->num_sms)); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CU(cudaLaunchKernelEx(&cfg, kernel, la, (int)n));
+      p->launches++;
+    };
     // conv2
     a = LayerArgs{};
     a.A = p->act1; a.W = p->w2; a.bias = p->b2; a.out = p->act2;
     a.M = n * s.o2h * s.o2w; a.K = 512; a.ldo = 64; a.scale = 1.0f;
     a.ih = s.o1h; a.iw = s.o1w; a.oh = s.o2h; a.ow = s.o2w;
-    launch_layer<CONV2, 64, EPI_RELU>(p, a, 64, st);
+    if (direct23) launch_direct(k_conv_direct<2>, dc_smem<2>(), a);
+    else launch_layer<CONV2, 64, EPI_RELU>(p, a, 64, st);
     // conv3
     a = LayerArgs{};
     a.A = p->act2; a.W = p->w3; a.bias = p->b3; a.out = p->act3;
     a.M = n * s.o3h * s.o3w; a.K = 576; a.ldo = 64; a.scale = 1.0f;
     a.ih = s.o2h; a.iw = s.o2w; a.oh = s.o3h; a.ow = s.o3w;
-    launch_layer<CONV3, 64, EPI_RELU>(p, a, 64, st);
+    if (direct23) launch_direct(k_conv_direct<3>, dc_smem<3>(), a);
+    else launch_layer<CONV3, 64, EPI_RELU>(p, a, 64, st);
     // linear -> 512 features + the two direct features
     a = LayerArgs{};
     a.A = p->act3; a.W = p->wfc; a.bias = p->bfc; a.out = p->feat;
@@ -1015,8 +1252,23 @@ extern "C" int32_t grp_buffer(grp_policy* p, const char* name, void** ptr, uint6
   if (k == "mu") { d = p->mu; sz = N * s.adim * 4; }
   else if (k == "log_std") { d = p->log_std; sz = N * s.adim * 4; }
   else if (k == "features") { d = p->feat; sz = N * FEAT_LD * 2; }
-  else if (k == "act1") { d = p->act1; sz = N * s.o1h * s.o1w * 32 * 2; }
-  else if (k == "act2") { d = p->act2; sz = N * s.o2h * s.o2w * 64 * 2; }
+  else if (k == "act1" || k == "act2") {
+    const int layer = k == "act1" ? 1 : 2;
+    sz = layer == 1 ? N * s.o1h * s.o1w * 32 * 2 : N * s.o2h * s.o2w * 64 * 2;
+    d = layer == 1 ? (void*)p->act1 : (void*)p->act2;
+    if (p->direct_last) {  // the last forward left them padded + swizzled: hand out a dense copy
+      __nv_bfloat16*& dense = layer == 1 ? p->act1_dense : p->act2_dense;
+      try {
+        CU(cudaSetDevice(p->device));
+        if (!dense) dense = palloc<__nv_bfloat16>(p, sz / 2);
+        CU(cudaDeviceSynchronize());  // the forward may have run on the caller's stream
+        k_unpack_act<<<1024, 256, 0, p->stream>>>(reinterpret_cast<const uint8_t*>(d), dense, p->last_n, layer);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(p->stream));
+      } catch (const std::exception& e) { g_err = e.what(); return 1; }
+      d = dense;
+    }
+  }
   else if (k == "act3") { d = p->act3; sz = N * (size_t)s.nflat * 2; }
   else if (k == "h1") { d = p->h1; sz = N * 256 * 2; }
   else if (k == "h2") { d = p->h2; sz = N * 256 * 2; }
