@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -745,6 +746,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) k_conv_direct(const LayerArgs a
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sbias[64];
+  if (threadIdx.x < 64) sbias[threadIdx.x] = __ldg(a.bias + threadIdx.x);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;                                  // NKB k-blocks x [64 rows x 128 B], SWIZZLE_128B
@@ -813,9 +816,6 @@ __global__ void __launch_bounds__(DC_THREADS, 1) k_conv_direct(const LayerArgs a
     // ---- epilogue: accumulator row m = 32 (warp % 4) + lane = 64 * image-in-pair + 8 * oy + ox, columns 32 (warp / 4) .. + 31
     const int half = warp >> 2, m = 32 * (warp & 3) + lane, img = m >> 6, oy = (m >> 3) & 7, ox = m & 7;
     const bool valid = oy < L::OUT && ox < L::OUT;
-    float eb[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) eb[i] = __ldg(a.bias + half * 32 + i);
     int k = 0;
     for (int pr = blockIdx.x; pr < npair; pr += gridDim.x, k++) {
       const int t = k & 1, n = 2 * pr + img;
@@ -828,6 +828,9 @@ __global__ void __launch_bounds__(DC_THREADS, 1) k_conv_direct(const LayerArgs a
       if (lane == 0) mbar_arrive(&bar_tempty[t]);  // the accumulator is in registers: the next pair's MMAs may overwrite it
       if (valid && n < nimg) {
         uint32_t o[16];
+        float eb[32];  // broadcast 16-byte loads from shared memory (the compiler re-issued global loads every pair when they were __ldg'ed up front)
+#pragma unroll
+        for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(eb + 4 * i) = *reinterpret_cast<const float4*>(sbias + half * 32 + 4 * i);
 #pragma unroll
         for (int i = 0; i < 16; i++) o[i] = pack_bf16(fmaxf(v[2 * i] + eb[2 * i], 0.0f), fmaxf(v[2 * i + 1] + eb[2 * i + 1], 0.0f));
         if (LAYER == 2) {
@@ -847,6 +850,161 @@ __global__ void __launch_bounds__(DC_THREADS, 1) k_conv_direct(const LayerArgs a
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------ actor MLP in one kernel
+// latent_pi.0 (576 -> 256, ReLU), latent_pi.2 (256 -> 256, ReLU) and the mu | log_std head (256 -> 16) for a tile of 128
+// observations, without the two trips of the hidden activations through HBM and without two of the three launches (the three
+// layers together are 3 % of the forward's flops but were a quarter of its time: each launch is latency, not work).
+// The hidden activations go TMEM -> registers (bias, ReLU, bf16) -> shared memory in the K-major SWIZZLE_128B layout, where
+// the next layer's MMAs read them as their A operand; the weights stream through a three-stage ring (cp.async, committed to
+// mbarriers by tcgen05.commit as in k_layer); one TMEM accumulator of 256 columns is reused by both hidden layers.
+struct MlpArgs {
+  const __nv_bfloat16 *feat, *W0, *W1, *Wh;   // [M][576], [256][576], [256][256], [16][256]
+  const float *b0, *b1, *bh;
+  int M, adim;
+  float *mu, *log_std, *action;
+  const float* noise;
+};
+constexpr int MF_STAGES = 3;
+constexpr int MF_A = BM * 128, MF_W = 256 * 128;                 // one k-block of A (128 rows) and of a 256-row weight matrix
+constexpr size_t MF_SMEM = MF_STAGES * (MF_A + MF_W) + 4 * MF_A + 1024;
+
+__global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const MlpArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_stage[MF_STAGES];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sb0[256], sb1[256], sbh[HEAD_N];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // MF_STAGES x [128 rows x 128 B]
+  uint8_t* sW = smem + MF_STAGES * MF_A;                // MF_STAGES x [256 rows x 128 B]
+  uint8_t* sH = smem + MF_STAGES * (MF_A + MF_W);       // hidden activations: 4 k-blocks x [128 rows x 128 B]
+  for (int i = tid; i < 256; i += THREADS) { sb0[i] = __ldg(a.b0 + i); sb1[i] = __ldg(a.b1 + i); }
+  if (tid < HEAD_N) sbh[tid] = __ldg(a.bh + tid);
+  if (tid == 0) {
+    for (int s = 0; s < MF_STAGES; s++) mbar_init(&bar_stage[s], 1);
+    mbar_init(&bar_done, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);  // columns 0-255: hidden-layer accumulator, 256-271: head
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const int m0 = blockIdx.x * BM;
+  const int row = m0 + warp * 32 + lane;      // this thread's accumulator row (epilogues)
+  const int r = warp * 32 + lane;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t idesc256 = instr_desc_f16(BM, 256, true), idesc16 = instr_desc_f16(BM, HEAD_N, true);
+
+  int g = 0;  // k-blocks staged so far over all three layers: stage = g % MF_STAGES, barrier phase = (g / MF_STAGES) & 1
+  // `wrows` rows of weight k-block kb (row stride K) -> stage, swizzled; optionally the A k-block from the feature matrix
+  auto copy_stage = [&](int gi, const __nv_bfloat16* W, int K, int kb, int wrows, bool with_a) {
+    const int s = gi % MF_STAGES;
+    const uint32_t dW = smem_u32(sW + s * MF_W);
+    for (int c = tid; c < wrows * 8; c += THREADS) {
+      const int wr = c >> 3, ch = c & 7;
+      cp_async16(dW + wr * 128 + ((ch ^ (wr & 7)) << 4), W + (size_t)wr * K + kb * BK + ch * 8, true);
+    }
+    if (with_a) {
+      const uint32_t dA = smem_u32(sA + s * MF_A);
+#pragma unroll
+      for (int i = 0; i < BM * 8 / THREADS; i++) {
+        const int c = i * THREADS + tid, ar = c >> 3, ch = c & 7;
+        const bool valid = m0 + ar < a.M;
+        cp_async16(dA + ar * 128 + ((ch ^ (ar & 7)) << 4), valid ? a.feat + (size_t)(m0 + ar) * FEAT_LD + kb * BK + ch * 8 : a.feat, valid);
+      }
+    }
+  };
+  // one layer: nkb k-blocks, A from the feature matrix (from_feat) or from sH, accumulator columns dcol .., N = wrows
+  auto run_layer = [&](const __nv_bfloat16* W, int K, int nkb, int wrows, bool from_feat, uint32_t dcol, uint32_t idesc, uint32_t done_parity) {
+    const int g0 = g;
+#pragma unroll 1
+    for (int kb = 0; kb < MF_STAGES - 1; kb++) {
+      if (kb < nkb) {
+        const int gi = g0 + kb;
+        if (gi >= MF_STAGES) { mbar_wait(&bar_stage[gi % MF_STAGES], ((gi / MF_STAGES) - 1) & 1); tc_fence_after(); }
+        copy_stage(gi, W, K, kb, wrows, from_feat);
+      }
+      cp_async_commit();
+    }
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; kb++) {
+      const int kn = kb + MF_STAGES - 1;
+      if (kn < nkb) {
+        const int gi = g0 + kn;
+        if (gi >= MF_STAGES) { mbar_wait(&bar_stage[gi % MF_STAGES], ((gi / MF_STAGES) - 1) & 1); tc_fence_after(); }
+        copy_stage(gi, W, K, kn, wrows, from_feat);
+      }
+      cp_async_commit();
+      cp_async_wait<MF_STAGES - 1>();
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const int s = (g0 + kb) % MF_STAGES;
+        tc_fence_after();
+        const uint32_t aaddr = from_feat ? smem_u32(sA + s * MF_A) : smem_u32(sH + kb * MF_A), baddr = smem_u32(sW + s * MF_W);
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++) umma_bf16(tmem + dcol, smem_desc_sw128(aaddr + k * 32), smem_desc_sw128(baddr + k * 32), idesc, (kb | k) != 0);
+        umma_commit(&bar_stage[s]);
+        if (kb == nkb - 1) umma_commit(&bar_done);
+      }
+    }
+    g = g0 + nkb;
+    mbar_wait(&bar_done, done_parity);
+    tc_fence_after();
+    __syncwarp();
+  };
+  // accumulator columns 0-255 -> bias, ReLU, bf16 -> sH (row r, k-block c0 / 64, 16-byte chunk (c0 % 64) / 8, swizzled)
+  auto hidden_epilogue = [&](const float* sb) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 16) {
+      float v[16], bv[16];
+      tmem_ld16(trow + c0, v);
+#pragma unroll
+      for (int k = 0; k < 4; k++) *reinterpret_cast<float4*>(bv + 4 * k) = *reinterpret_cast<const float4*>(sb + c0 + 4 * k);
+      uint32_t o[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) o[k] = pack_bf16(fmaxf(v[2 * k] + bv[2 * k], 0.0f), fmaxf(v[2 * k + 1] + bv[2 * k + 1], 0.0f));
+      uint8_t* dst = sH + (c0 >> 6) * MF_A + r * 128;
+      const int j = (c0 & 63) >> 3;
+      *reinterpret_cast<uint4*>(dst + ((j ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(dst + (((j + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    fence_async_smem();   // generic-proxy writes of sH -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  };
+  run_layer(a.W0, FEAT_LD, FEAT_LD / BK, 256, true, 0, idesc256, 0);
+  hidden_epilogue(sb0);
+  run_layer(a.W1, 256, 256 / BK, 256, false, 0, idesc256, 1);
+  hidden_epilogue(sb1);
+  run_layer(a.Wh, 256, 256 / BK, HEAD_N, false, 256, idesc16, 0);
+  {
+    float v[16];
+    tmem_ld16(trow + 256, v);
+    if (row < a.M) {
+      for (int k = 0; k < a.adim; k++) {
+        const float mu = v[k] + sbh[k];
+        float ls = v[8 + k] + sbh[8 + k];
+        ls = fminf(fmaxf(ls, -20.0f), 2.0f);  // stable-baselines3 sac/policies.py LOG_STD_MIN / LOG_STD_MAX
+        float pre = mu;
+        if (a.noise) pre += __expf(ls) * a.noise[(size_t)row * a.adim + k];
+        a.mu[(size_t)row * a.adim + k] = mu;
+        a.log_std[(size_t)row * a.adim + k] = ls;
+        a.action[(size_t)row * a.adim + k] = tanhf(pre);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // padded / swizzled activations -> dense NHWC (tests and debugging only: grp_buffer("act1" / "act2"))
@@ -1011,6 +1169,7 @@ extern "C" grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t he
 #define SET_SMEM(M_, BN_, E_) CU(cudaFuncSetAttribute(k_layer<M_, BN_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer_smem_bytes<M_, BN_>()))
     SET_SMEM(CONV1, 32, EPI_RELU);
     CU(cudaFuncSetAttribute(k_conv1_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM));
+    CU(cudaFuncSetAttribute(k_mlp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MF_SMEM));
     CU(cudaFuncSetAttribute(k_conv_direct<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem<2>()));
     CU(cudaFuncSetAttribute(k_conv_direct<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem<3>()));
     CU(cudaFuncSetAttribute(k_conv1_direct<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD_SMEM));
@@ -1155,6 +1314,13 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     CU(cudaSetDevice(p->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
     const Shape& s = p->sh;
+    // GRP_EVENTS=1 (development aid): an event after every launch; grp_forward then blocks and prints the time between them
+    static const bool ev_on = getenv("GRP_EVENTS") != nullptr;
+    cudaEvent_t evs[9]; int nev = 0;
+    auto mark = [&]() { if (ev_on && nev < 9) { cudaEventCreate(&evs[nev]); cudaEventRecord(evs[nev], st); nev++; } };
+    struct EvPrint { bool on; cudaEvent_t* e; int* n; ~EvPrint() { if (!on || *n < 2) return; cudaEventSynchronize(e[*n - 1]); fprintf(stderr, "[grp_forward]");
+      for (int i = 1; i < *n; i++) { float ms = 0; cudaEventElapsedTime(&ms, e[i - 1], e[i]); fprintf(stderr, " %.1f us", ms * 1e3f); } fprintf(stderr, "\n"); for (int i = 0; i < *n; i++) cudaEventDestroy(e[i]); } } evp{ev_on, evs, &nev};
+    mark();
     LayerArgs a{};
     // conv1: uint8 planes -> [n*o1h*o1w][32]
     a.A = obs_dev; a.W = p->w1; a.bias = p->b1; a.out = p->act1;
@@ -1192,6 +1358,7 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     } else {
       launch_layer<CONV1, 32, EPI_RELU>(p, a, 32, st);
     }
+    mark();
     auto launch_direct = [&](auto kernel, size_t smem_bytes, const LayerArgs& la) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(std::min((n + 1) / 2, p->num_sms)); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
@@ -1209,6 +1376,7 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     a.ih = s.o1h; a.iw = s.o1w; a.oh = s.o2h; a.ow = s.o2w;
     if (direct23) launch_direct(k_conv_direct<2>, dc_smem<2>(), a);
     else launch_layer<CONV2, 64, EPI_RELU>(p, a, 64, st);
+    mark();
     // conv3
     a = LayerArgs{};
     a.A = p->act2; a.W = p->w3; a.bias = p->b3; a.out = p->act3;
@@ -1216,12 +1384,30 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     a.ih = s.o2h; a.iw = s.o2w; a.oh = s.o3h; a.ow = s.o3w;
     if (direct23) launch_direct(k_conv_direct<3>, dc_smem<3>(), a);
     else launch_layer<CONV3, 64, EPI_RELU>(p, a, 64, st);
+    mark();
     // linear -> 512 features + the two direct features
     a = LayerArgs{};
     a.A = p->act3; a.W = p->wfc; a.bias = p->bfc; a.out = p->feat;
     a.M = n; a.K = s.nflat; a.lda = s.nflat; a.ldo = FEAT_LD; a.scale = 1.0f;
     a.C = s.C; a.H = s.H; a.W_ = s.W; a.obs = obs_dev;
     launch_layer<DENSE, 128, EPI_FEATURES>(p, a, 512, st);
+    mark();
+    const char* mlp = getenv("GRP_MLP");  // "layers" = one kernel per layer (writes h1 / h2); default = fused
+    if (!(mlp && !strcmp(mlp, "layers"))) {
+      MlpArgs ma{};
+      ma.feat = p->feat; ma.W0 = p->wp0; ma.W1 = p->wp1; ma.Wh = p->wh; ma.b0 = p->bp0; ma.b1 = p->bp1; ma.bh = p->bh;
+      ma.M = n; ma.adim = s.adim; ma.mu = p->mu; ma.log_std = p->log_std; ma.action = actions_dev; ma.noise = noise_dev;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((n + BM - 1) / BM); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = MF_SMEM; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CU(cudaLaunchKernelEx(&cfg, k_mlp_fused, ma));
+      p->launches++;
+      mark();
+      return 0;
+    }
     // latent_pi
     a = LayerArgs{};
     a.A = p->feat; a.W = p->wp0; a.bias = p->bp0; a.out = p->h1;

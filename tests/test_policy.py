@@ -65,7 +65,7 @@ def test_cuda_policy_matches_golden(tag, C):
     assert np.abs(act - g[tag + "_action"]).max() <= TOL_ACTION
     sto = pol(obs, deterministic=False, noise=torch.as_tensor(g[tag + "_noise"], device="cuda")).cpu().numpy()
     assert np.abs(sto - g[tag + "_action_stochastic"]).max() <= 2 * TOL_ACTION
-    assert pol.launch_count == 14  # 7 layer kernels per forward
+    assert pol.launch_count == 10  # 5 kernels per forward: conv1, conv2, conv3, linear (+ direct features), fused actor MLP
     pol.close()
 
 
