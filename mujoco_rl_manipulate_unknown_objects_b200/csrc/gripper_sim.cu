@@ -58,6 +58,7 @@ struct grs_sim {
   grs_config cfg{};
   EnvCfg ecfg{};
   cudaStream_t stream = nullptr;
+  cudaStream_t last_dev_stream = nullptr;  // caller's stream of the last device-path call that has not been joined yet
   SimBuffers b{};
   RenderScene scene{};
   DevModel* d_model = nullptr;
@@ -305,6 +306,7 @@ extern "C" int32_t grs_reset(grs_sim* s, const uint8_t* mask_dev, void* stream) 
   try {
     CU(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    if (st != s->stream) s->last_dev_stream = st;  // a later host-path call (own stream) must order itself behind this one
     const int wpb = 8;
     k_reset<<<(s->n + wpb - 1) / wpb, wpb * 32, 0, st>>>(s->b, s->ecfg, mask_dev);
     CU(cudaGetLastError());
@@ -315,12 +317,23 @@ extern "C" int32_t grs_reset(grs_sim* s, const uint8_t* mask_dev, void* stream) 
   } catch (const std::exception& e) { return fail(e.what()); }
 }
 
+
+// The *_host entry points run on the simulator's own (non-blocking) stream and end synchronised; the device-path entry points run
+// on the caller's stream.  Mixing them on one simulator is legal: a host-path call first joins the caller's stream.
+static void join_device_path(grs_sim* s) {
+  if (s->last_dev_stream) {
+    CU(cudaStreamSynchronize(s->last_dev_stream));
+    s->last_dev_stream = nullptr;
+  }
+}
+
 extern "C" int32_t grs_step(grs_sim* s, const float* actions_dev, void* stream) {
   GUARD(s);
   if (!actions_dev) return fail("actions pointer is null");
   try {
     CU(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    if (st != s->stream) s->last_dev_stream = st;  // a later host-path call (own stream) must order itself behind this one
     launch_queue_kernel_prep(s, st);
     if (s->ev_n == grs_sim::NEV) harvest_events(s);
     CU(cudaEventRecord(s->ev0[s->ev_n], st));
@@ -359,6 +372,7 @@ extern "C" int32_t grs_step_host(grs_sim* s, const float* actions_host, uint8_t*
   if (!actions_host) return fail("actions pointer is null");
   try {
     CU(cudaSetDevice(s->device));
+    join_device_path(s);
     const size_t N = s->n, ob = (size_t)s->C * s->H * s->W;
     CU(cudaMemcpyAsync(s->d_actions, actions_host, N * s->adim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     // pinned destination buffers are written by the observation phase itself, environment by environment as their agent
@@ -399,6 +413,8 @@ extern "C" int32_t grs_step_host(grs_sim* s, const float* actions_host, uint8_t*
 extern "C" int32_t grs_reset_host(grs_sim* s, uint8_t* obs_host, float* achieved_host, float* desired_host) {
   GUARD(s);
   try {
+    CU(cudaSetDevice(s->device));
+    join_device_path(s);
     if (grs_reset(s, nullptr, nullptr) != 0) return 1;
     const size_t N = s->n, ob = (size_t)s->C * s->H * s->W;
     if (obs_host) CU(cudaMemcpyAsync(obs_host, s->d_obs, N * ob, cudaMemcpyDeviceToHost, s->stream));
@@ -415,6 +431,7 @@ extern "C" int32_t grs_substep(grs_sim* s, int32_t n, void* stream) {
   try {
     CU(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    if (st != s->stream) s->last_dev_stream = st;  // a later host-path call (own stream) must order itself behind this one
     launch_queue_kernel_prep(s, st);
     k_substep<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, n);
     CU(cudaGetLastError());
@@ -652,6 +669,7 @@ extern "C" int32_t grs_render(grs_sim* s, int32_t camera_id, int32_t width, int3
   try {
     CU(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    if (st != s->stream) s->last_dev_stream = st;  // a later host-path call (own stream) must order itself behind this one
     launch_queue_kernel_prep(s, st);
     k_camera_state<<<s->grid, WARPS_PER_BLOCK * 32, s->smem, st>>>(s->b, camera_id);
     CU(cudaGetLastError());
