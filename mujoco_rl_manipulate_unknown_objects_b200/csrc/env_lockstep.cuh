@@ -299,18 +299,35 @@ __global__ void __launch_bounds__(LS_MAX_THREADS, GRS_LS_MINBLOCKS) k_env_step_l
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     atomicAdd(s.sm_phys + (smid & 255), 1);
   }
-  const DevModel& m = stage_model(s.model);
+  // Block staging by the TMA engine: the compiled model (2.3 KB) and, when they fit beside two blocks' workspaces, the convex-hull
+  // vertices of every geom (<= 18.7 KB; the support scans of the collision stage then cost shared-memory latency instead of
+  // L1/L2 round trips, which were half of that stage's stall samples) arrive as two bulk asynchronous copies (cp.async.bulk,
+  // 1-D) that complete on one mbarrier; no thread touches the bytes on their way in.
+  __shared__ unsigned long long stage_bar;
+  const float4* hull = s.hull;
+  {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+    constexpr unsigned model_bytes = (sizeof(DevModel) + 15) / 16 * 16;
+    const unsigned hull_off = model_bytes + (unsigned)(blockDim.x >> 5) * (unsigned)sizeof(WS), hull_bytes = s.hull_smem ? (unsigned)s.hull_count * 16u : 0u;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(model_bytes + hull_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((unsigned)__cvta_generic_to_shared(grs_smem)), "l"(s.model), "r"(model_bytes), "r"(bar) : "memory");
+      if (hull_bytes)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(grs_smem + hull_off)), "l"(s.hull), "r"(hull_bytes), "r"(bar) : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+    if (s.hull_smem) hull = reinterpret_cast<const float4*>(grs_smem + hull_off);
+  }
+  const DevModel& m = *reinterpret_cast<const DevModel*>(grs_smem);
   WS& w = my_ws();
   const int lane = threadIdx.x & 31;
-  // convex-hull vertices of every geom -> shared memory (behind the workspaces): the support scans of the collision stage
-  // then cost shared-memory latency instead of L1/L2 round trips (they were half of that stage's stall samples)
-  const float4* hull = s.hull;
-  if (s.hull_smem) {
-    float4* hs = reinterpret_cast<float4*>(grs_smem + (sizeof(DevModel) + 15) / 16 * 16 + (size_t)(blockDim.x >> 5) * sizeof(WS));
-    for (int i = threadIdx.x; i < s.hull_count; i += blockDim.x) hs[i] = s.hull[i];
-    hull = hs;
-    __syncthreads();
-  }
   __shared__ unsigned long long t_sum[8], t_max[8], t_round[8];
   __shared__ unsigned long long t_rounds, t_lone[8], t_lone_rounds;  // rounds in which exactly one warp of the block was active
   __shared__ unsigned int t_hist[12];  // rounds with k active warps (k = 0..11)

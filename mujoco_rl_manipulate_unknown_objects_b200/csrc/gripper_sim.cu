@@ -147,7 +147,7 @@ extern "C" grs_sim* grs_create(const char* xml_path, int32_t num_envs, const grs
     std::vector<float> hv;
     std::vector<int> adj;
     build_dev_model(s->hm, dm, hv, adj);
-    s->d_model = dalloc<DevModel>(s.get(), 1);
+    s->d_model = (DevModel*)dalloc<unsigned char>(s.get(), (sizeof(DevModel) + 15) / 16 * 16);  // the step kernel bulk-copies it in 16-byte units
     CU(cudaMemcpy(s->d_model, &dm, sizeof dm, cudaMemcpyHostToDevice));
     s->d_hull = dalloc<float4>(s.get(), hv.size() / 4 + 1);
     CU(cudaMemcpy(s->d_hull, hv.data(), hv.size() * sizeof(float), cudaMemcpyHostToDevice));

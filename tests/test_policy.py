@@ -140,3 +140,34 @@ def test_cuda_policy_rejects_bad_input():
     with pytest.raises(ValueError):
         pol.load_state_dict(sd)
     pol.close()
+
+
+@pytest.mark.gpu
+def test_kernel_variants_agree(monkeypatch):
+    """The development switches select other implementations of the same layers (im2col-per-image / generic gather conv1,
+    gather-based conv2 / conv3, one kernel per MLP layer).  Every path must reproduce the default path's activations and actions
+    to bf16 accumulation noise — they share weights, layouts seen from outside and epilogues, not code."""
+    import torch
+    from mujoco_rl_manipulate_unknown_objects_b200.policy import GripperPolicy
+    n = 77  # odd: the descriptor-addressed conv2 / conv3 work on image pairs
+    pol = GripperPolicy(max_envs=n, obs_shape=(5, 64, 64), action_dim=6, params=_params(5, 11))
+    obs = torch.randint(0, 256, (n, 5, 64, 64), dtype=torch.uint8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+
+    def run():
+        act = pol(obs).cpu().numpy()
+        return (act, pol.mu[:n].cpu().numpy(), pol.features[:n].float().cpu().numpy(),
+                pol.buffer("act1", (n, 15, 15, 32), torch.bfloat16).float().cpu().numpy(), pol.buffer("act2", (n, 6, 6, 64), torch.bfloat16).float().cpu().numpy(),
+                pol.buffer("act3", (n, 4, 4, 64), torch.bfloat16).float().cpu().numpy())
+    ref = run()
+    for env in ({"GRP_CONV23": "gather"}, {"GRP_CONV1": "image"}, {"GRP_CONV1": "generic"}, {"GRP_MLP": "layers"}, {"GRP_CONV1_ISSUER": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = run()
+        for k in env:
+            monkeypatch.delenv(k)
+        errs = [float(np.abs(a - b).max()) for a, b in zip(out, ref)]
+        print(env, "max |diff| action %.1e mu %.1e features %.1e act1 %.1e act2 %.1e act3 %.1e" % tuple(errs))
+        assert errs[0] <= 5e-3 and errs[1] <= 1e-2 and errs[2] <= 2e-2, (env, errs)
+        scale = [max(1.0, float(np.abs(r).max())) for r in ref[3:]]
+        assert all(e <= 0.02 * s_ for e, s_ in zip(errs[3:], scale)), (env, errs)
+    pol.close()
