@@ -80,6 +80,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -711,6 +712,169 @@ __global__ void __launch_bounds__(CD_THREADS + (DEDICATED ? 32 : 0), 1) k_conv1_
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// The same convolution, warp-specialised: converting the next image, multiplying the current one and writing out the previous
+// one are three different sets of warps that meet only at mbarriers, instead of one set of warps doing the three jobs one after
+// the other between block barriers (k_conv1_direct: 46 % of its stall samples sat at __syncthreads, tensor pipe active 34 %).
+//   warp  17     producer: the image's four uint8 planes (16 KB, contiguous) by cp.async.bulk into a 4-deep raw ring — 64 KB per SM in
+//                flight from HBM: with register prefetch two images ahead the kernel was bound by memory latency (1.7 TB/s)
+//   warps 0-7    converters: raw ring -> fp16 copy of image k in stage k % 3, fence.proxy.async, one arrive per warp on full[stage]
+//   warp  16     MMA issuer: waits full[stage] and tempty[acc], 16 x tcgen05.mma (N = 96), tcgen05.commit -> empty[stage], tfull[acc]
+//   warps 8-15   epilogue: tcgen05.ld of accumulator k % 2 (even | Wa | Wb column blocks), arrive tempty[acc], lane shuffle for the
+//                odd columns, bias + ReLU, bf16, stores in the layout conv2 reads
+constexpr int CW_THREADS = 18 * 32;
+constexpr int CW_STAGES = 3;       // fp16 image copies
+constexpr int CW_ACC = 2;          // TMEM accumulators (128 columns each; 4 measured no faster: the kernel is bound by the issue rate of its 16 worker warps)
+constexpr int CW_RAW = 4;          // uint8 images in flight from HBM (16 KB each): 64 KB per SM outstanding
+constexpr size_t CW_SMEM = CD_W + CW_STAGES * CD_STAGE + CW_RAW * 16384 + 1024;
+
+__global__ void __launch_bounds__(CW_THREADS, 1) k_conv1_ws(const LayerArgs a, int nimg) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[CW_STAGES], bar_empty[CW_STAGES], bar_tfull[CW_ACC], bar_tempty[CW_ACC], bar_rfull[CW_RAW], bar_rempty[CW_RAW];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;                                   // [4 k-blocks][96 rows: W | Wa | Wb][128 B]
+  uint8_t* st0 = smem + CD_W;                           // stage s: the fp16 image at st0 + s * CD_STAGE
+  uint8_t* raw0 = st0 + CW_STAGES * CD_STAGE;           // raw ring: the four uint8 planes of an image, 16 KB each
+  if (tid == 0) {
+    for (int i = 0; i < CW_STAGES; i++) { mbar_init(&bar_full[i], 8); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < CW_ACC; i++) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 8); }
+    for (int i = 0; i < CW_RAW; i++) { mbar_init(&bar_rfull[i], 1); mbar_init(&bar_rempty[i], 8); }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base_s, 128 * CW_ACC);  // accumulator t: columns 128 t .. 128 t + 95
+  for (int i = tid; i < 4 * 96 * 8; i += CW_THREADS) {  // weights: parameters, staged before the dependency wait
+    const int kb = i / 768, c = i - kb * 768, row = c >> 3, ch = c & 7;
+    cp_async16(smem_u32(sB + kb * 96 * 128 + row * 128 + ((ch ^ (row & 7)) << 4)), a.W + (size_t)row * a.K + kb * BK + ch * 8, true);
+  }
+  cp_async_commit();
+  for (int i = tid; i < CW_STAGES * 1024 / 16; i += CW_THREADS) *reinterpret_cast<uint4*>(st0 + (i >> 6) * CD_STAGE + (CD_STAGE - 1024) + (i & 63) * 16) = make_uint4(0, 0, 0, 0);
+  cp_async_wait<0>();
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const int stride = gridDim.x;
+  if (warp == 17) {
+    // ---- producer: the image planes (one contiguous 16 KB block of the [n][C][64][64] uint8 tensor) by bulk copy, CW_RAW images ahead
+    if (lane == 0) {
+      const unsigned char* obs = reinterpret_cast<const unsigned char*>(a.A);
+      const size_t img_bytes = (size_t)a.C * 4096;
+      int k = 0;
+#pragma unroll 1
+      for (int n = blockIdx.x; n < nimg; n += stride, k++) {
+        const int rs = k % CW_RAW;
+        mbar_wait(&bar_rempty[rs], ((k / CW_RAW) & 1) ^ 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_rfull[rs])), "r"(16384) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(raw0 + rs * 16384)), "l"(obs + (size_t)n * img_bytes), "r"(16384), "r"(smem_u32(&bar_rfull[rs])) : "memory");
+      }
+    }
+  } else if (warp < 8) {
+    // ---- converters: uint8 -> fp16, chunk q = 8 pixels at byte 8 q of the raw image, byte 16 q of the copy
+    int k = 0;
+#pragma unroll 1
+    for (int n = blockIdx.x; n < nimg; n += stride, k++) {
+      const int s = k % CW_STAGES, rs = k % CW_RAW;
+      mbar_wait(&bar_rfull[rs], (k / CW_RAW) & 1);
+      uint2 raw[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) raw[j] = *reinterpret_cast<const uint2*>(raw0 + rs * 16384 + (tid + 256 * j) * 8);
+      mbar_wait(&bar_empty[s], ((k / CW_STAGES) & 1) ^ 1);
+      uint8_t* E = st0 + s * CD_STAGE;
+#pragma unroll
+      for (int j = 0; j < 8; j++) *reinterpret_cast<uint4*>(E + (tid + 256 * j) * 16) = u8x8_to_f16x8(raw[j]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bar_full[s]); mbar_arrive(&bar_rempty[rs]); }
+    }
+  } else if (warp == 16) {
+    // ---- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_f16(BM, 96, false);
+      const uint64_t b0 = smem_desc_sw128(smem_u32(sB));
+      const uint32_t blo = (uint32_t)b0, bhi = (uint32_t)(b0 >> 32);
+      int k = 0;
+#pragma unroll 1
+      for (int n = blockIdx.x; n < nimg; n += stride, k++) {
+        const int s = k % CW_STAGES, t = k % CW_ACC;
+        mbar_wait(&bar_tempty[t], ((k / CW_ACC) & 1) ^ 1);
+        mbar_wait(&bar_full[s], (k / CW_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t a0 = smem_desc_nosw(smem_u32(st0 + s * CD_STAGE), 128, 512);
+        const uint32_t alo = (uint32_t)a0, ahi = (uint32_t)(a0 >> 32), td = tmem + t * 128;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+          for (int kyp = 0; kyp < 4; kyp++) {
+            if ((c | kyp) == 0) umma_bf16_lo<0>(td, alo + ((c * 8192 + kyp * 256) >> 4), ahi, blo + ((c * 96 * 128 + kyp * 32) >> 4), bhi, idesc);
+            else umma_bf16_lo<1>(td, alo + ((c * 8192 + kyp * 256) >> 4), ahi, blo + ((c * 96 * 128 + kyp * 32) >> 4), bhi, idesc);
+          }
+        umma_commit(&bar_empty[s]);
+        umma_commit(&bar_tfull[t]);
+      }
+    }
+  } else {
+    // ---- epilogue: accumulator row m = 32 (warp % 4) + lane = 8 oy + r, output channels 16 half .. + 15 of pixels ox = 2r and 2r + 1
+    const int ew = warp - 8, half = ew >> 2, em = 32 * (ew & 3) + lane, eoy = em >> 3, er = em & 7;
+    const bool evalid = eoy < 15;
+    float eb[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) eb[i] = __ldg(a.bias + half * 16 + i);
+    const float escale = a.scale;
+    int k = 0;
+#pragma unroll 1
+    for (int n = blockIdx.x; n < nimg; n += stride, k++) {
+      const int t = k % CW_ACC;
+      mbar_wait(&bar_tfull[t], (k / CW_ACC) & 1);
+      tc_fence_after();
+      float ve[16], va[16], vb[16];
+      const uint32_t tb = tmem + t * 128 + half * 16 + ((uint32_t)(32 * (ew & 3)) << 16);
+      tmem_ld16(tb, ve);
+      tmem_ld16(tb + 32, va);
+      tmem_ld16(tb + 64, vb);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[t]);
+#pragma unroll
+      for (int i = 0; i < 16; i++) va[i] += __shfl_down_sync(0xffffffffu, vb[i], 1);  // odd(r) = chunk r x Wa + chunk r + 1 x Wb
+      if (evalid) {
+        uint32_t oe[8], oo[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          oe[i] = pack_bf16(fmaxf(fmaf(ve[2 * i], escale, eb[2 * i]), 0.0f), fmaxf(fmaf(ve[2 * i + 1], escale, eb[2 * i + 1]), 0.0f));
+          oo[i] = pack_bf16(fmaxf(fmaf(va[2 * i], escale, eb[2 * i]), 0.0f), fmaxf(fmaf(va[2 * i + 1], escale, eb[2 * i + 1]), 0.0f));
+        }
+        if (a.ldo == 32) {  // dense [225][32] rows (the gather-based conv2)
+          __nv_bfloat16* row = a.out + ((size_t)n * 225 + eoy * 15 + 2 * er) * 32 + half * 16;
+          reinterpret_cast<uint4*>(row)[0] = make_uint4(oe[0], oe[1], oe[2], oe[3]);
+          reinterpret_cast<uint4*>(row)[1] = make_uint4(oe[4], oe[5], oe[6], oe[7]);
+          if (er < 7) {
+            reinterpret_cast<uint4*>(row + 32)[0] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+            reinterpret_cast<uint4*>(row + 32)[1] = make_uint4(oo[4], oo[5], oo[6], oo[7]);
+          }
+        } else {
+          // [15][16 px][32 ch]: 128-byte lines of two pixels (2r, 2r + 1), chunk j of line l stored at position j ^ (l & 7)
+          const int l = eoy * 8 + er;
+          uint8_t* line = reinterpret_cast<uint8_t*>(a.out) + (size_t)n * 16384 + l * 128;
+#pragma unroll
+          for (int g = 0; g < 2; g++) {
+            *reinterpret_cast<uint4*>(line + (((half * 2 + g) ^ (l & 7)) << 4)) = make_uint4(oe[4 * g], oe[4 * g + 1], oe[4 * g + 2], oe[4 * g + 3]);
+            if (er < 7) *reinterpret_cast<uint4*>(line + (((4 + half * 2 + g) ^ (l & 7)) << 4)) = make_uint4(oo[4 * g], oo[4 * g + 1], oo[4 * g + 2], oo[4 * g + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128 * CW_ACC);
+}
+
 // ------------------------------------------------------------------------------------------------ conv2 / conv3 without im2col
 // Same idea with the 128-byte swizzle.  The previous layer leaves its activations in HBM in exactly the byte order the tensor
 // core wants to find them in shared memory (padded NHWC lines of 128 bytes, 16-byte chunks XOR-swizzled by the line index), so
@@ -737,7 +901,6 @@ constexpr int DC_THREADS = 320;  // warps 0-7 epilogue, warp 8 producer, warp 9 
 template <int LAYER>
 constexpr size_t dc_smem() { return (size_t)DirectConv<LAYER>::NKB * 64 * 128 + (size_t)DirectConv<LAYER>::STAGES * 2 * DirectConv<LAYER>::IMG_IN + 8192 + 1024; }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
 template <int LAYER>
 __global__ void __launch_bounds__(DC_THREADS, 1) k_conv_direct(const LayerArgs a, int nimg) {
@@ -1172,6 +1335,7 @@ extern "C" grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t he
     CU(cudaFuncSetAttribute(k_mlp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MF_SMEM));
     CU(cudaFuncSetAttribute(k_conv_direct<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem<2>()));
     CU(cudaFuncSetAttribute(k_conv_direct<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem<3>()));
+    CU(cudaFuncSetAttribute(k_conv1_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
     CU(cudaFuncSetAttribute(k_conv1_direct<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD_SMEM));
     CU(cudaFuncSetAttribute(k_conv1_direct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD_SMEM));
     CU(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -1329,7 +1493,7 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     const bool image_kernel = s.H == 64 && s.W == 64 && s.cin == 4 && !getenv("GRP_CONV1_GENERIC");
     const char* c1 = getenv("GRP_CONV1");  // development switch: "image" = im2col per image, "generic" = gather layer; default = descriptor-addressed
     const char* cc = getenv("GRP_CONV23");  // "gather" = im2col-on-the-fly conv2 / conv3 (k_layer); default = descriptor-addressed when conv1 is
-    const bool direct1 = image_kernel && !(c1 && (!strcmp(c1, "image") || !strcmp(c1, "generic")));
+    const bool direct1 = image_kernel && !(c1 && (!strcmp(c1, "image") || !strcmp(c1, "generic")));  // "sync" is a direct variant too
     const bool direct23 = direct1 && !(cc && !strcmp(cc, "gather"));
     p->direct_last = direct23; p->last_n = n;
     if (direct23) a.ldo = 0;  // conv1 leaves act1 in the padded, swizzled layout conv2's descriptor reads
@@ -1337,6 +1501,15 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
       // no im2col: the tensor core reads the (fp16) image rows through its shared-memory descriptor (k_conv1_direct)
       cudaLaunchConfig_t cfg{};
       const bool dedicated = getenv("GRP_CONV1_ISSUER") && atoi(getenv("GRP_CONV1_ISSUER")) != 0;
+      if (!(c1 && !strcmp(c1, "sync"))) {  // default: warp-specialised; GRP_CONV1=sync selects the block-barrier version
+        cfg.gridDim = dim3(std::min(n, p->num_sms)); cfg.blockDim = dim3(CW_THREADS); cfg.dynamicSmemBytes = CW_SMEM; cfg.stream = st;
+        cudaLaunchAttribute attrw[1];
+        attrw[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrw[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attrw; cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, k_conv1_ws, a, (int)n));
+        p->launches++;
+      } else {
       cfg.gridDim = dim3(std::min(n, p->num_sms)); cfg.blockDim = dim3(CD_THREADS + (dedicated ? 32 : 0)); cfg.dynamicSmemBytes = CD_SMEM; cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1345,6 +1518,7 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
       if (dedicated) CU(cudaLaunchKernelEx(&cfg, k_conv1_direct<true>, a, (int)n));
       else CU(cudaLaunchKernelEx(&cfg, k_conv1_direct<false>, a, (int)n));
       p->launches++;
+      }
     } else if (image_kernel && !(c1 && !strcmp(c1, "generic"))) {
       // one image per CTA, planes staged by a bulk copy (k_conv1_image); any other observation shape takes the generic layer
       cudaLaunchConfig_t cfg{};

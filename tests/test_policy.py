@@ -159,7 +159,8 @@ def test_kernel_variants_agree(monkeypatch):
                 pol.buffer("act1", (n, 15, 15, 32), torch.bfloat16).float().cpu().numpy(), pol.buffer("act2", (n, 6, 6, 64), torch.bfloat16).float().cpu().numpy(),
                 pol.buffer("act3", (n, 4, 4, 64), torch.bfloat16).float().cpu().numpy())
     ref = run()
-    for env in ({"GRP_CONV23": "gather"}, {"GRP_CONV1": "image"}, {"GRP_CONV1": "generic"}, {"GRP_MLP": "layers"}, {"GRP_CONV1_ISSUER": "1"}):
+    for env in ({"GRP_CONV23": "gather"}, {"GRP_CONV1": "sync"}, {"GRP_CONV1": "sync", "GRP_CONV1_ISSUER": "1"}, {"GRP_CONV1": "image"}, {"GRP_CONV1": "generic"},
+                {"GRP_MLP": "layers"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         out = run()
