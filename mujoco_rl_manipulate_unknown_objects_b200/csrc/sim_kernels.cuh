@@ -500,7 +500,7 @@ __device__ __forceinline__ void expand_portal(WS& w, int lane) {
   sup_copy(w, dst, 4, lane);
 }
 // closest point of triangle (a,b,c) to the origin (Ericson, Real-Time Collision Detection 5.1.5)
-__device__ __noinline__ float origin_tri_closest(const float* a, const float* b, const float* c, float* w) {
+__device__ __forceinline__ float origin_tri_closest(const float* a, const float* b, const float* c, float* w) {
   float ab[3], ac[3];
   for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
   float d1 = -dot3(ab, a), d2 = -dot3(ac, a);
@@ -524,7 +524,7 @@ __device__ __noinline__ float origin_tri_closest(const float* a, const float* b,
   return sqrtf(dot3(w, w));
 }
 // libccd mpr.c : findPos — contact position from the portal's barycentric coordinates of the origin
-__device__ __noinline__ void find_pos(const WS& w, float* pos) {
+__device__ __forceinline__ void find_pos(const WS& w, float* pos) {
   float dir[3], b[4], t[3], sum;
   portal_dir(w, dir);
   cross3(t, SUPV(1), SUPV(2)); b[0] = dot3(t, SUPV(3));
@@ -949,8 +949,11 @@ __device__ __noinline__ void make_constraint(const DevModel& m, WS& w, int lane)
 }
 
 // -------------------------------------------------------------------------------- Newton solver
+// The small helpers of the solver loop (constraint update, line-search evaluation, the 13-wide products, the Hessian) are inlined
+// into solve_newton: as separate functions their call overhead and the register shuffling around every call were 4 % of the step
+// (profiles/r2zf_inline.log); the stage functions themselves stay out of line (inlining them into the kernel body costs 6 %).
 // engine_solver.c : mj_constraintUpdate — lane = item (limit row or contact). Returns the constraint cost (warp-uniform).
-__device__ __noinline__ float constraint_update(WS& w, int lane, bool want_cone_hessian) {
+__device__ __forceinline__ float constraint_update(WS& w, int lane, bool want_cone_hessian) {
   const int nlim = w.nlim, nitem = nlim + w.ncon;
   float cost = 0;
   int state = 0;
@@ -1005,7 +1008,7 @@ __device__ __noinline__ float constraint_update(WS& w, int lane, bool want_cone_
 }
 
 // derivative and curvature of the cost along qacc + alpha*search (engine_solver.c : PrimalEval)
-__device__ __noinline__ void line_eval(const WS& w, int lane, float alpha, float q1, float q2, float& d1, float& d2) {
+__device__ __forceinline__ void line_eval(const WS& w, int lane, float alpha, float q1, float q2, float& d1, float& d2) {
   const int nlim = w.nlim, nitem = nlim + w.ncon;
   float D1 = 0, D2 = 0;
   if (lane < nlim) {
@@ -1035,7 +1038,7 @@ __device__ __noinline__ void line_eval(const WS& w, int lane, float alpha, float
 }
 
 // y_i = sum_k M[i][k] x[k] for lane i < NV (x in shared memory)
-__device__ __noinline__ float mat13_vec(const float* M, const float* x, int lane) {
+__device__ __forceinline__ float mat13_vec(const float* M, const float* x, int lane) {
   float v = 0;
   if (lane < NV) {
     const float* row = M + lane * NV;
@@ -1045,7 +1048,7 @@ __device__ __noinline__ float mat13_vec(const float* M, const float* x, int lane
   return v;
 }
 // out[r] = J[r] . x - sub[r]  for every constraint row (sub may be NULL)
-__device__ __noinline__ void rows_dot(const WS& w, const float* x, const float* sub, float* out, int lane) {
+__device__ __forceinline__ void rows_dot(const WS& w, const float* x, const float* sub, float* out, int lane) {
 #pragma unroll 1
   for (int r = lane; r < w.nefc; r += 32) {
     const float* row = w.u.con.J[r];
@@ -1056,7 +1059,7 @@ __device__ __noinline__ void rows_dot(const WS& w, const float* x, const float* 
   }
 }
 // f_i = sum_r J[r][i] force[r]  (lane i < NV)
-__device__ __noinline__ float jt_force(const WS& w, int lane) {
+__device__ __forceinline__ float jt_force(const WS& w, int lane) {
   float fc = 0;
   if (lane < NV) {
 #pragma unroll 4
@@ -1075,7 +1078,7 @@ __constant__ unsigned char HESS_TRI[91] = {
 
 // Hessian H = M + J^T diag(act*D) J + cone blocks (lower triangle only), engine_solver.c : MakeHessian / HessianCone.
 // w.e_act holds act*D per row.  One lane per lower-triangle entry: 2 passes when the trees are uncoupled, 3 otherwise.
-__device__ __noinline__ void make_hessian(WS& w, int lane) {
+__device__ __forceinline__ void make_hessian(WS& w, int lane) {
   const int nefc = w.nefc, nlim = w.nlim, ncon = w.ncon;
   const int nent = w.coupled ? 91 : 49;
 #pragma unroll 1

@@ -19,9 +19,15 @@ CASES = [("sugar_cube", 0, {}, 3), ("sugar_cube", 45, {}, 4), ("sand_ball", 0, {
 
 
 # MEASURED (round 2, B200, 48 matched agent steps per case): steps in which the fp32 trajectory leaves the fp64 one by > 1e-4 or takes a
-# different number of substeps ("flipped by contact chaos": a grasping step is a discontinuous map).  Asserted: measured + 50 %.
-MEASURED_FLIPS = {"sugar_cube-0-default": 10, "sugar_cube-45-default": 6, "sand_ball-0-default": 2, "bread_crumb-0-default": 1, "acorn-0-default": 1,
-                  "sand_ball-45-include_roll": 5, "sugar_cube-0-her_buffer-time_horizon": 7, "gripper_two_fingers-0-default": 5, "sugar_cube-120-default": 4}
+# different number of substeps ("flipped by contact chaos": a grasping step is a discontinuous map).  WHICH steps flip depends on
+# the last bit of the fp32 arithmetic: the two builds measured this round (before / after the solver helpers were inlined, which
+# changes FMA contraction) gave per-case counts (10 6 2 1 1 5 7 5 4) and (11 5 4 4 0 6 6 9 6), totals 41 and 51 of 432.  Asserted:
+# per case the larger of the two measurements + 50 % + 2 (small-number noise), and over all cases a total of at most 60 (14 % of the
+# steps; 1.5 sigma above the larger total).
+MEASURED_FLIPS = {"sugar_cube-0-default": 11, "sugar_cube-45-default": 6, "sand_ball-0-default": 4, "bread_crumb-0-default": 4, "acorn-0-default": 1,
+                  "sand_ball-45-include_roll": 6, "sugar_cube-0-her_buffer-time_horizon": 7, "gripper_two_fingers-0-default": 9, "sugar_cube-120-default": 6}
+MAX_TOTAL_FLIPS = 60
+_FLIPS_SEEN = {}
 
 
 def make(scene, direction, kw, n, auto_reset=False):
@@ -114,9 +120,20 @@ def test_agent_step_at_matched_states(scene, direction, kw, seed):
         scene, direction, kw, N, flipped, int(info[:, I["NSUB_A"]:I["NSUB_A"] + 3].sum()), np.median(qerrs), max(qerrs), np.median(rew_err), max(rew_err),
         sum(1 for r in ref if r["reward"] > 0)))
     case = "%s-%d-%s" % (scene, direction, "-".join(kw) or "default")
-    assert flipped <= int(np.ceil(1.5 * MEASURED_FLIPS[case])), "flip count %d regressed against the measured %d" % (flipped, MEASURED_FLIPS[case])
+    _FLIPS_SEEN[case] = flipped
+    assert flipped <= int(np.ceil(1.5 * MEASURED_FLIPS[case])) + 2, "flip count %d regressed against the measured %d" % (flipped, MEASURED_FLIPS[case])
     assert sum(1 for r in ref if r["reward"] > 0) > 0
     sim.close()
+
+
+@pytest.mark.gpu
+def test_total_flip_count_over_all_cases():
+    """Runs after the parametrised cases above (file order): the sum of their flip counts against the measured total."""
+    if len(_FLIPS_SEEN) < len(MEASURED_FLIPS):
+        pytest.skip("needs every case of test_agent_step_at_matched_states in the same session")
+    total = sum(_FLIPS_SEEN.values())
+    print("\nflipped agent steps over all cases: %d of %d (measured 41 and 51)" % (total, 48 * len(MEASURED_FLIPS)))
+    assert total <= MAX_TOTAL_FLIPS, _FLIPS_SEEN
 
 
 def test_free_rollout_follows_the_golden_reference_until_contact():

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_policy.py -m gpu -x -q 2>&1 | tail -2
-timeout 300 python tools/policy_bench.py 4096 16384 2>&1 | tee gpurun_out/r2_policy_bench.log
+python -m pytest tests -m gpu -q 2>&1 | tail -12 | tee gpurun_out/r2zh_tests.log
+python -m pytest tests/test_env_parity.py -m gpu -q -s 2>&1 | grep -E "flipped agent"
