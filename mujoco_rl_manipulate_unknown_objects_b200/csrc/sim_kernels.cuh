@@ -1206,9 +1206,12 @@ __device__ __noinline__ int solve_newton(const DevModel& m, WS& w, int lane, int
     cost = gs + constraint_update(w, lane, true);
     improvement = scale * (old - cost);
   }
-  // final constraint force in joint space
-  float fc = jt_force(w, lane);
-  if (lane < NV) w.fcon[lane] = fc;
+  // final constraint force in joint space: w.fcon is current on every exit through a break (it was computed at the top of that
+  // iteration and nothing moved since); only running into the iteration cap leaves it one update behind
+  if (iter == max_iter) {
+    float fc = jt_force(w, lane);
+    if (lane < NV) w.fcon[lane] = fc;
+  }
   __syncwarp();
   return iter;
 }
