@@ -1,1 +1,1 @@
-ncu --set full --clock-control none -k regex:"k_conv1_ws|k_conv_direct" --launch-skip 9 -c 3 -o gpurun_out/r2_policy_convs python tools/policy_bench.py 4096 > gpurun_out/r2_ncu_convs.log 2>&1
+for v in 1 2 3 4 5; do echo "== ablation $v"; GRS_LIB=$PWD/tools/_libA$v.so GRP_EVENTS=1 timeout 120 python tools/policy_bench.py 4096 2>&1 | grep grp_forward | tail -1; done
