@@ -1,4 +1,5 @@
-for v in 0 1; do echo "== GRS_HESS_FP64=$v"; GRS_HESS_FP64=$v python -m pytest tests/test_physics_parity.py -m gpu -q -s -k "matched_states" 2>&1 | grep -E "outlier|\[.*\]|passed|failed" | cut -c1-220; done
-export PRE=150 K=30
-GRS_HESS_FP64=1 python tools/steady_diag.py acorn 4096 2>&1 | cut -c1-200
-python tools/steady_diag.py acorn 4096 2>&1 | cut -c1-200
+# round-end check on a GPU box: /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/_call.sh'
+set -x
+python -m pytest tests -m gpu -q 2>&1 | tail -3 | tee gpurun_out/tests.log
+python __graft_entry__.py smoke 2>&1 | tail -1
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_short.json 2> gpurun_out/bench.err; tail -c 200 gpurun_out/bench_short.json
