@@ -1015,6 +1015,178 @@ __global__ void __launch_bounds__(DC_THREADS, 1) k_conv_direct(const LayerArgs a
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// ------------------------------------------------------------------------------------------------ conv2 + conv3 in one kernel
+// conv2's output never leaves the SM: its epilogue writes act2 (two images, 16 KB) into shared memory in exactly the padded,
+// swizzled layout conv3's descriptors read, and the same MMA-issuer thread then runs conv3 on it.  Both weight matrices are resident
+// (64 + 72 KB).  That removes act2's trip through L2 / HBM (8 KB per observation each way) and one launch with its fixed cost.
+//   warp 8   producer: act1 image pairs by cp.async.bulk into a 2-deep ring
+//   warp 9   issuer, per pair k: conv2(k) [32 MMAs -> accumulator k % 2], then conv3(k - 1) [36 MMAs on the act2 buffer -> accumulator
+//            2 + (k - 1) % 2]; tcgen05.commit hands back the act1 stage / the act2 buffer and publishes the accumulators
+//   warps 0-7 epilogue, per pair k: conv2 accumulator -> bias, ReLU, bf16 -> act2 buffer (fence.proxy.async, arrive), then the conv3
+//            accumulator of pair k - 1 -> act3 in HBM (dense rows for the linear layer)
+constexpr int C23_STAGES = 2;
+constexpr size_t C23_W2 = 8 * 64 * 128, C23_W3 = 9 * 64 * 128, C23_PAIR1 = 32768, C23_PAIR2 = 16384;
+constexpr size_t C23_SMEM = C23_W2 + C23_W3 + C23_STAGES * C23_PAIR1 + C23_PAIR2 + 4096 + 1024;
+
+struct Conv23Args {
+  const uint8_t* act1;                       // [n][15][16 px][32 ch] padded, pre-swizzled (conv1's output)
+  const __nv_bfloat16 *W2, *W3;              // [64][512], [64][576] K-major
+  const float *b2, *b3;
+  __nv_bfloat16* act3;                       // [n][16][64]
+};
+
+__global__ void __launch_bounds__(DC_THREADS, 1) k_conv23_fused(const Conv23Args a, int nimg) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[C23_STAGES], bar_empty[C23_STAGES], bar_t2full[2], bar_t2empty[2], bar_t3full[2], bar_t3empty[2], bar_a2full, bar_a2empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sb2[64], sb3[64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW2 = smem;
+  uint8_t* sW3 = sW2 + C23_W2;
+  uint8_t* sA1 = sW3 + C23_W3;                       // C23_STAGES x act1 pair; the junk groups of the last stage read on into sA2
+  uint8_t* sA2 = sA1 + C23_STAGES * C23_PAIR1;       // act2 pair [2][8][8 px][64 ch] (+ 4 KB behind it for conv3's junk groups)
+  if (tid < 64) { sb2[tid] = __ldg(a.b2 + tid); sb3[tid] = __ldg(a.b3 + tid); }
+  if (tid == 0) {
+    for (int i = 0; i < C23_STAGES; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&bar_t2full[i], 1); mbar_init(&bar_t2empty[i], 8); mbar_init(&bar_t3full[i], 1); mbar_init(&bar_t3empty[i], 8); }
+    mbar_init(&bar_a2full, 8); mbar_init(&bar_a2empty, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);  // columns 0-63, 64-127: conv2 accumulators; 128-191, 192-255: conv3
+  for (int i = tid; i < 8 * 64 * 8; i += DC_THREADS) {
+    const int kb = i >> 9, row = (i >> 3) & 63, ch = i & 7;
+    cp_async16(smem_u32(sW2 + kb * 64 * 128 + row * 128 + ((ch ^ (row & 7)) << 4)), a.W2 + (size_t)row * 512 + kb * BK + ch * 8, true);
+  }
+  for (int i = tid; i < 9 * 64 * 8; i += DC_THREADS) {
+    const int kb = i >> 9, row = (i >> 3) & 63, ch = i & 7;
+    cp_async16(smem_u32(sW3 + kb * 64 * 128 + row * 128 + ((ch ^ (row & 7)) << 4)), a.W3 + (size_t)row * 576 + kb * BK + ch * 8, true);
+  }
+  cp_async_commit();
+  for (int i = tid; i < (int)(C23_PAIR2 + 4096) / 16; i += DC_THREADS) *reinterpret_cast<uint4*>(sA2 + i * 16) = make_uint4(0, 0, 0, 0);  // padding lines stay zero
+  cp_async_wait<0>();
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const int npair = (nimg + 1) >> 1;
+  if (warp == 8) {
+    if (lane == 0) {
+      int k = 0;
+      for (int pr = blockIdx.x; pr < npair; pr += gridDim.x, k++) {
+        const int s = k % C23_STAGES;
+        mbar_wait(&bar_empty[s], ((k / C23_STAGES) & 1) ^ 1);
+        const uint32_t bytes = (2 * pr + 1 < nimg) ? (uint32_t)C23_PAIR1 : (uint32_t)C23_PAIR1 / 2;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_full[s])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sA1 + s * C23_PAIR1)), "l"(a.act1 + (size_t)pr * C23_PAIR1), "r"(bytes), "r"(smem_u32(&bar_full[s])) : "memory");
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_f16(BM, 64, true);
+      const uint64_t w2 = smem_desc_sw128(smem_u32(sW2)), w3 = smem_desc_sw128(smem_u32(sW3));
+      uint64_t a2d = smem_desc_sw128(smem_u32(sA2));  // conv3: 8-row groups one padded image row (1024 B) apart = the default SBO
+      auto conv3 = [&](int k) {  // on the act2 buffer written by the epilogue of pair k
+        const int t = k & 1;
+        mbar_wait(&bar_t3empty[t], ((k >> 1) & 1) ^ 1);
+        mbar_wait(&bar_a2full, k & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 9; kb++)
+#pragma unroll
+          for (int k16 = 0; k16 < 4; k16++)
+            umma_bf16(tmem + 128 + t * 64, a2d + (uint64_t)((((kb / 3) * 8 + (kb % 3)) * 128 + k16 * 32) >> 4), w3 + (uint64_t)((kb * 64 * 128 + k16 * 32) >> 4), idesc, (kb | k16) != 0);
+        umma_commit(&bar_a2empty);
+        umma_commit(&bar_t3full[t]);
+      };
+      int k = 0;
+      for (int pr = blockIdx.x; pr < npair; pr += gridDim.x, k++) {
+        const int s = k % C23_STAGES, t = k & 1;
+        mbar_wait(&bar_t2empty[t], ((k >> 1) & 1) ^ 1);
+        mbar_wait(&bar_full[s], (k / C23_STAGES) & 1);
+        tc_fence_after();
+        uint64_t a1d = smem_desc_sw128(smem_u32(sA1 + s * C23_PAIR1));
+        a1d = (a1d & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(2048 >> 4) << 32);  // conv2: 8-row groups two image rows apart
+#pragma unroll
+        for (int kb = 0; kb < 8; kb++)
+#pragma unroll
+          for (int k16 = 0; k16 < 4; k16++)
+            umma_bf16(tmem + t * 64, a1d + (uint64_t)(((kb >> 1) * 1024 + (kb & 1) * 128 + k16 * 32) >> 4), w2 + (uint64_t)((kb * 64 * 128 + k16 * 32) >> 4), idesc, (kb | k16) != 0);
+        umma_commit(&bar_empty[s]);
+        umma_commit(&bar_t2full[t]);
+        if (k > 0) conv3(k - 1);
+      }
+      if (k > 0) conv3(k - 1);
+    }
+  } else {
+    // accumulator row m = 32 (warp % 4) + lane = 64 * image-in-pair + 8 * oy + ox, columns 32 (warp / 4) .. + 31
+    const int half = warp >> 2, m = 32 * (warp & 3) + lane, img = m >> 6, oy = (m >> 3) & 7, ox = m & 7;
+    const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
+    auto epi3 = [&](int k, int pr) {  // conv3 accumulator of pair k -> act3
+      const int t = k & 1, n = 2 * pr + img;
+      mbar_wait(&bar_t3full[t], (k >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + 128 + t * 64 + half * 32 + tlane, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_t3empty[t]);
+      if (oy < 4 && ox < 4 && n < nimg) {
+        float eb[32];
+#pragma unroll
+        for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(eb + 4 * i) = *reinterpret_cast<const float4*>(sb3 + half * 32 + 4 * i);
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) o[i] = pack_bf16(fmaxf(v[2 * i] + eb[2 * i], 0.0f), fmaxf(v[2 * i + 1] + eb[2 * i + 1], 0.0f));
+        uint4* dst = reinterpret_cast<uint4*>(a.act3 + ((size_t)n * 16 + oy * 4 + ox) * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 4; j++) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+    };
+    int k = 0, prev_pr = 0;
+    for (int pr = blockIdx.x; pr < npair; pr += gridDim.x, k++) {
+      const int t = k & 1;
+      mbar_wait(&bar_t2full[t], (k >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + t * 64 + half * 32 + tlane, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_t2empty[t]);
+      uint32_t o[16];
+      {
+        float eb[32];
+#pragma unroll
+        for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(eb + 4 * i) = *reinterpret_cast<const float4*>(sb2 + half * 32 + 4 * i);
+#pragma unroll
+        for (int i = 0; i < 16; i++) o[i] = pack_bf16(fmaxf(v[2 * i] + eb[2 * i], 0.0f), fmaxf(v[2 * i + 1] + eb[2 * i + 1], 0.0f));
+      }
+      mbar_wait(&bar_a2empty, (k & 1) ^ 1);  // conv3 of the previous pair has read the act2 buffer
+      if (oy < 6 && ox < 6) {
+        // [8][8 px][64 ch] lines of 128 bytes per image, chunk j of line l at position j ^ (l & 7) (what conv3's descriptor reads)
+        const int l = oy * 8 + ox;
+        uint8_t* line = sA2 + img * 8192 + l * 128;
+#pragma unroll
+        for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(line + (((half * 4 + j) ^ (l & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a2full);
+      if (k > 0) epi3(k - 1, prev_pr);
+      prev_pr = pr;
+    }
+    if (k > 0) epi3(k - 1, prev_pr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // ------------------------------------------------------------------------------------------------ actor MLP in one kernel
 // latent_pi.0 (576 -> 256, ReLU), latent_pi.2 (256 -> 256, ReLU) and the mu | log_std head (256 -> 16) for a tile of 128
 // observations, without the two trips of the hidden activations through HBM and without two of the three launches (the three
@@ -1244,6 +1416,7 @@ struct grp_policy {
   __nv_bfloat16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *feat = nullptr, *h1 = nullptr, *h2 = nullptr;
   __nv_bfloat16 *act1_dense = nullptr, *act2_dense = nullptr;  // grp_buffer("act1" / "act2") when the descriptor-addressed chain left them padded + swizzled
   bool direct_last = false;   // layout of act1 / act2 after the last forward
+  bool act2_valid = true;     // false when conv2 + conv3 ran fused (act2 never reached HBM)
   int last_n = 0;
   float *mu = nullptr, *log_std = nullptr;
   std::vector<void*> owned;
@@ -1333,6 +1506,7 @@ extern "C" grp_policy* grp_create(int32_t max_envs, int32_t channels, int32_t he
     SET_SMEM(CONV1, 32, EPI_RELU);
     CU(cudaFuncSetAttribute(k_conv1_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1_SMEM));
     CU(cudaFuncSetAttribute(k_mlp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MF_SMEM));
+    CU(cudaFuncSetAttribute(k_conv23_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C23_SMEM));
     CU(cudaFuncSetAttribute(k_conv_direct<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem<2>()));
     CU(cudaFuncSetAttribute(k_conv_direct<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dc_smem<3>()));
     CU(cudaFuncSetAttribute(k_conv1_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM));
@@ -1543,6 +1717,23 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
       CU(cudaLaunchKernelEx(&cfg, kernel, la, (int)n));
       p->launches++;
     };
+    // GRP_CONV23=fused: conv2 + conv3 in one kernel, act2 stays on the SM.  Measured equal to the two kernels (46 us against 26.6 + 26.6
+    // event-timed, the forward 0.115 ms either way: both are bound by the rate of N = 64 MMAs, not by act2's traffic), so the default
+    // stays the split pair, whose intermediate the tests can read.
+    const bool fused23 = direct23 && cc && !strcmp(cc, "fused");
+    if (fused23) {
+      Conv23Args ca{};
+      ca.act1 = reinterpret_cast<const uint8_t*>(p->act1); ca.W2 = p->w2; ca.W3 = p->w3; ca.b2 = p->b2; ca.b3 = p->b3; ca.act3 = p->act3;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(std::min((n + 1) / 2, p->num_sms)); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = C23_SMEM; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CU(cudaLaunchKernelEx(&cfg, k_conv23_fused, ca, (int)n));
+      p->launches++;
+      mark(); mark();
+    } else {
     // conv2
     a = LayerArgs{};
     a.A = p->act1; a.W = p->w2; a.bias = p->b2; a.out = p->act2;
@@ -1559,6 +1750,8 @@ extern "C" int32_t grp_forward(grp_policy* p, const uint8_t* obs_dev, float* act
     if (direct23) launch_direct(k_conv_direct<3>, dc_smem<3>(), a);
     else launch_layer<CONV3, 64, EPI_RELU>(p, a, 64, st);
     mark();
+    }
+    p->act2_valid = !fused23;
     // linear -> 512 features + the two direct features
     a = LayerArgs{};
     a.A = p->act3; a.W = p->wfc; a.bias = p->bfc; a.out = p->feat;
@@ -1614,6 +1807,7 @@ extern "C" int32_t grp_buffer(grp_policy* p, const char* name, void** ptr, uint6
   else if (k == "features") { d = p->feat; sz = N * FEAT_LD * 2; }
   else if (k == "act1" || k == "act2") {
     const int layer = k == "act1" ? 1 : 2;
+    if (layer == 2 && !p->act2_valid) { g_err = "act2 does not exist after a forward with the fused conv2 + conv3 kernel (GRP_CONV23=split|gather keeps it)"; return 1; }
     sz = layer == 1 ? N * s.o1h * s.o1w * 32 * 2 : N * s.o2h * s.o2w * 64 * 2;
     d = layer == 1 ? (void*)p->act1 : (void*)p->act2;
     if (p->direct_last) {  // the last forward left them padded + swizzled: hand out a dense copy

@@ -159,6 +159,15 @@ def test_kernel_variants_agree(monkeypatch):
                 pol.buffer("act1", (n, 15, 15, 32), torch.bfloat16).float().cpu().numpy(), pol.buffer("act2", (n, 6, 6, 64), torch.bfloat16).float().cpu().numpy(),
                 pol.buffer("act3", (n, 4, 4, 64), torch.bfloat16).float().cpu().numpy())
     ref = run()
+    # conv2 + conv3 in one kernel (act2 never reaches HBM, so it cannot be read back in that mode)
+    monkeypatch.setenv("GRP_CONV23", "fused")
+    act_f = pol(obs).cpu().numpy()
+    with pytest.raises(RuntimeError):
+        pol.buffer("act2", (n, 6, 6, 64), torch.bfloat16)
+    act3_f = pol.buffer("act3", (n, 4, 4, 64), torch.bfloat16).float().cpu().numpy()
+    monkeypatch.delenv("GRP_CONV23")
+    print("fused conv2 + conv3: max |diff| action %.1e act3 %.1e" % (float(np.abs(act_f - ref[0]).max()), float(np.abs(act3_f - ref[5]).max())))
+    assert np.array_equal(act_f, ref[0]) and np.array_equal(act3_f, ref[5])
     for env in ({"GRP_CONV23": "gather"}, {"GRP_CONV1": "sync"}, {"GRP_CONV1": "sync", "GRP_CONV1_ISSUER": "1"}, {"GRP_CONV1": "image"}, {"GRP_CONV1": "generic"},
                 {"GRP_MLP": "layers"}):
         for k, v in env.items():
