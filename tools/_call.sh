@@ -1,1 +1,1 @@
-timeout 120 tools/micro/umma_rate 2>&1 | tee gpurun_out/r2_umma_rate.log
+timeout 200 tools/micro/bulk_stream 2>&1 | tee gpurun_out/r2_bulk_stream.log
