@@ -29,6 +29,60 @@ def test_archive_round_trip_keeps_sb3_names(tmp_path):
         np.testing.assert_array_equal(actor[name].numpy(), params[name])
 
 
+def test_reads_an_archive_laid_out_like_sb3_save_to_zip_file(tmp_path):
+    """Independent of this repo's writer: an archive assembled the way stable-baselines3's `save_to_zip_file` lays it out for an
+    off-policy SAC model with a custom features extractor — JSON `data` whose non-JSON entries are {":type:", ":serialized:"}
+    (base64 cloudpickle), `policy.pth` holding actor, critic and critic_target with the features extractor repeated under each,
+    separate optimizer state dicts, `pytorch_variables.pth`, the version file and `system_info.txt` (SB3 >= 1.5).  stable-baselines3
+    itself is not installed here, so this pins the READER to the published layout, not to SB3's code."""
+    import base64
+    import collections
+    import io
+    import cloudpickle
+    import torch
+    params = init_params(channels=5, action_dim=6, n_flatten=1024, seed=9)
+    sd = collections.OrderedDict()
+    for k, v in params.items():
+        sd["actor." + k] = torch.as_tensor(v)
+    fe = {k: torch.as_tensor(v) for k, v in params.items() if k.startswith("features_extractor.")}
+    for net in ("critic", "critic_target"):
+        for k, v in fe.items():
+            sd[net + "." + k] = v.clone()
+        for q in ("qf0", "qf1"):
+            for i, (o, n) in enumerate(((256, 514 + 6), (256, 256), (1, 256))):
+                sd["%s.%s.%d.weight" % (net, q, 2 * i)] = torch.zeros(o, n)
+                sd["%s.%s.%d.bias" % (net, q, 2 * i)] = torch.zeros(o)
+
+    def ser(obj):
+        return {":type:": str(type(obj)), ":serialized:": base64.b64encode(cloudpickle.dumps(obj)).decode()}
+    data = {"policy_class": ser(dict), "verbose": 1, "policy_kwargs": ser({"features_extractor_class": dict, "net_arch": [256, 256]}),
+            "observation_space": ser(("Dict", (5, 64, 64))), "action_space": ser(("Box", 6)), "n_envs": 1, "num_timesteps": 100000,
+            "buffer_size": 10000, "batch_size": 256, "learning_starts": 100, "tau": 0.005, "gamma": 0.99, "gradient_steps": 1,
+            "lr_schedule": ser(lambda _: 3e-4), "target_entropy": -6.0, "ent_coef": "auto", "_last_obs": None}
+
+    def pth(obj):
+        b = io.BytesIO()
+        torch.save(obj, b)
+        return b.getvalue()
+    path = tmp_path / "best_model.zip"
+    with zipfile.ZipFile(path, "w") as z:
+        z.writestr("data", json.dumps(data, indent=4))
+        z.writestr("pytorch_variables.pth", pth({"log_ent_coef": torch.zeros(1)}))
+        z.writestr("policy.pth", pth(sd))
+        for opt in ("actor.optimizer", "critic.optimizer", "ent_coef_optimizer"):
+            z.writestr(opt + ".pth", pth({"state": {}, "param_groups": [{"lr": 3e-4, "params": [0]}]}))
+        z.writestr("_stable_baselines3_version", "1.6.2")
+        z.writestr("system_info.txt", "OS: Linux\nPython: 3.9\nStable-Baselines3: 1.6.2\nPyTorch: 1.12\nGym: 0.21.0\n")
+    got, meta = sb3_io.read_sb3_zip(str(tmp_path / "best_model"))
+    assert meta["gamma"] == 0.99 and meta["policy_kwargs"][":type:"].startswith("<class")
+    actor = sb3_io.actor_state_dict(got)
+    assert sorted(actor) == sorted(n for n, _ in param_spec())
+    for name, shape in param_spec():
+        assert tuple(actor[name].shape) == shape
+        np.testing.assert_array_equal(actor[name].numpy(), params[name])
+    assert "critic_target.qf1.4.weight" in got and "critic.features_extractor.cnn.0.weight" in got
+
+
 def test_archive_errors(tmp_path):
     p = tmp_path / "not_a_model.zip"
     with zipfile.ZipFile(p, "w") as z:
