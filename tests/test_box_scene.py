@@ -57,3 +57,36 @@ def test_plane_box_contacts_at_rest_and_tilted():
     d2.forward_position()
     fb = [c for c in d2.contacts() if c["geom1"] == 0 and c["geom2"] == box]
     assert len(fb) == 2 and all(abs(c["dist"]) < 1e-9 for c in fb)
+
+
+def test_friction_cone_obeys_coulomb_at_the_stick_slip_threshold():
+    """Analytic pin of the oracle's elliptic friction cone (no MuJoCo needed): a 1 kg box on the floor, pair friction 1, pushed
+    horizontally at its base (force at the centre of mass + the torque that moves its line of action to the floor).  Below mu*m*g
+    it must stay put (soft-constraint creep only), just above it must accelerate with (F - mu*m*g)/m."""
+    from oracle import engine, mjcf
+    md = mjcf.compile_mjcf(os.path.join(XMLS, "gripper_two_fingers.xml"))
+    m = engine.Model(md)
+    ob = md["body_names"].index("object")
+    mass, g, h = md["body_mass"][ob], 9.81, 0.2
+    assert abs(mass - 1.0) < 1e-12
+
+    def push(mult, nsteps=100):
+        d = engine.Data(m)
+        d.reset()
+        d.xfrc_applied[m.body_id("ee"), 2] = 0.438 * g   # gripper hovers (robot_env.py:64-65), never touches the box here
+        d.step(600)                                        # the box settles on its four corner contacts
+        assert d.ncon == 4 and abs(d.qvel[7:13]).max() < 1e-6
+        F = mult * mass * g
+        d.xfrc_applied[ob, 0] = F
+        d.xfrc_applied[ob, 4] = -h * F
+        v = []
+        for _ in range(nsteps):
+            d.step()
+            v.append(d.qvel[7])
+        return np.array(v), d
+    for mult in (0.5, 0.95):
+        v, d = push(mult)
+        assert d.ncon == 4 and abs(v).max() < 1e-3, (mult, abs(v).max())      # free motion would reach 0.98 / 1.86 m/s
+    v, d = push(1.05)
+    accel = (v[-1] - v[19]) / (80 * 0.002)
+    assert d.ncon >= 2 and abs(accel - 0.05 * g) < 0.05 * 0.05 * g + 0.02, accel   # 0.4905 m/s^2 expected; measured 0.498
