@@ -174,3 +174,20 @@ def test_free_body_conserves_angular_momentum():
     assert np.abs(L - L[0]).max() / np.linalg.norm(L[0]) < 1e-3      # measured 2.9e-4
     assert abs(E[-1] - E[0]) / E[0] < 5e-4                           # measured 4.5e-5
     assert np.abs(np.diff(d.qvel[10:13] - [3.0, 1.0, 2.0])).max() > 1e-3   # the body does tumble: w itself is NOT constant
+
+
+def test_gravity_compensation_leaves_the_documented_residual():
+    """robot_env.py:64-65 holds the gripper up with a constant +z force of 0.438 * 9.81 N on `ee`; the meshes weigh 0.44719 kg, so 9.2 g
+    of weight remain and the gripper sinks at the terminal velocity of its damped z slide: (m - 0.438) g / damping(gripper_z = 20).
+    Pins the mesh masses, the xfrc term of the smooth forces and the implicit joint damping in one number."""
+    md = mjcf.compile_mjcf(scene_file("acorn"))
+    m = engine.Model(md)
+    names = md["body_names"]
+    gm = sum(md["body_mass"][names.index(n)] for n in ("ee", "robotiq_85_base_link", "left_inner_knuckle", "left_inner_finger",
+                                                       "right_inner_knuckle", "right_inner_finger"))
+    d = engine.Data(m)
+    d.reset()
+    d.xfrc_applied[m.body_id("ee"), 2] = 0.438 * 9.81
+    d.step(400)   # 0.8 s = 36 time constants (m / damping = 22 ms)
+    assert abs(d.qvel[2] + (gm - 0.438) * 9.81 / 20.0) < 1e-9
+    assert abs(d.qvel[:2]).max() < 1e-9 and abs(d.qvel[3:7]).max() < 1e-6
