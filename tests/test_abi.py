@@ -110,3 +110,20 @@ def test_info_record_layout_matches_the_header():
         nxt += 1
     assert values == _native.INFO
     assert _native.INFO["STRIDE"] == 40 and _native.STATE_STRIDE == 64 and _native.RENDER_STATE_STRIDE == 96
+
+
+def test_micro_benchmarks_compile_for_sm_100a(tmp_path):
+    """tools/micro/*.cu (tcgen05.mma rate against N, per-SM bulk-copy streaming rate: the measurements DESIGN.md §3.3 quotes) build
+    with the flags of the library; they only RUN on a B200."""
+    import glob
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    srcs = sorted(glob.glob(os.path.join(ROOT, "tools", "micro", "*.cu")))
+    assert len(srcs) >= 2
+    for src in srcs:
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-c", "-o", str(tmp_path / "m.o"), src],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
