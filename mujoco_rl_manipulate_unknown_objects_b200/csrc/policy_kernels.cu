@@ -5,8 +5,15 @@
 //   obs u8 [N,C,H,W] --/255--> conv 8x8 s4 (C-1 -> 32) ReLU -> conv 4x4 s2 (32 -> 64) ReLU -> conv 3x3 s1 (64 -> 64) ReLU
 //   -> flatten -> linear (-> 512) ReLU -> concat obs[:, C-1, 0, 0:2]/255 (514) -> 256 ReLU -> 256 ReLU -> mu | log_std -> tanh
 //
-// Every layer is ONE kernel template, k_layer<MODE, BN, EPI>: an implicit GEMM  D[128 x BN] += A[128 x 64] * W[BN x 64]^T
-// per k-block, with
+// Kernels of one forward (default path, the reference's 64 x 64 x 4 observation):
+//   k_conv1_ws          conv1 WITHOUT im2col: the tensor core reads the fp16 image through a no-swizzle shared-memory descriptor,
+//                       16 MMAs (M 128, N 96 = W | Wa | Wb) per image; warp-specialised (TMA producer, converters, issuer, epilogue)
+//   k_conv_direct<2|3>  conv2 / conv3 WITHOUT im2col: the previous layer's padded, pre-swizzled activations arrive by one bulk copy per
+//                       image pair and every k-block is a start address inside that copy (k_conv23_fused: both in one kernel)
+//   k_layer<DENSE>      the linear layer (+ the two direct features): the generic implicit-GEMM layer described next
+//   k_mlp_fused         latent_pi.0, latent_pi.2 and the mu | log_std head; hidden activations TMEM -> registers -> shared memory
+// k_layer<MODE, BN, EPI> is round 1's generic layer (still used for the linear layer, for other observation shapes and behind the
+// GRP_* switches): an implicit GEMM  D[128 x BN] += A[128 x 64] * W[BN x 64]^T per k-block, with
 //   * A gathered by the CTA's threads straight from the previous layer's activations (im2col on the fly, NHWC bf16; the
 //     first layer reads the uint8 observation planes and converts) into the canonical K-major SWIZZLE_128B shared-memory
 //     layout that tcgen05.mma reads through a shared-memory descriptor,
